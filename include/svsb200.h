@@ -1,0 +1,138 @@
+/* svsb200.h -- C ABI of libsvsb200.so: the B200-native Vamana batched-search hot path.
+ *
+ * This is the drop-in boundary for the reference's Vamana search.  Each
+ * entry point names the reference interface it replaces (file:line relative to
+ * /root/reference).  Plain pointers and sizes only -- no C++/torch types -- so it binds
+ * from C++ (scalablevectorsearch_b200/cpp/gpu_vamana_index.h), Python ctypes
+ * (scalablevectorsearch_b200/_lib.py) or anything else with a C FFI.
+ *
+ * Conventions
+ *   * every function returns 0 on success, non-zero on failure; svsb200_last_error()
+ *     gives the message for the calling thread (the C++ adapter rethrows it as
+ *     svs::ANNException, matching include/svs/lib/exception.h);
+ *   * there is no CPU fallback: if no sm_100-class device is usable, create/search fail;
+ *   * "host" pointers may be pageable or pinned; "device" pointers must live on the
+ *     index's device;
+ *   * ids are the reference's internal uint32 ids (core/graph/graph.h:388) widened to
+ *     `id_bytes` (4 or 8; the orchestrator boundary uses size_t, orchestrators/manager.h:79).
+ */
+#ifndef SVSB200_H
+#define SVSB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVSB200_VERSION 100
+
+/* Element types: svs::DataType float32 / float16 / int8 / uint8 (lib/datatype.h). */
+enum { SVSB200_F32 = 0, SVSB200_F16 = 1, SVSB200_I8 = 2, SVSB200_U8 = 3 };
+/* svs::DistanceType (core/distance.h:41-60): L2, MIP, Cosine. */
+enum { SVSB200_L2 = 0, SVSB200_IP = 1, SVSB200_COSINE = 2 };
+/* Storage of the base vectors:
+ *   PLAIN  svs::data::SimpleData<T>                       (core/data/simple.h:259-618)
+ *   SQ     svs::quantization::scalar::SQDataset<int8|uint8> (quantization/scalar/scalar.h:363-551);
+ *          aux = {scale, bias}
+ *   LVQ8   one-level 8-bit locally-adaptive quantisation (closed-source in the reference,
+ *          own specification: DESIGN.md §LVQ-8); aux = per-dataset mean[dim] */
+enum { SVSB200_PLAIN = 0, SVSB200_SQ = 1, SVSB200_LVQ8 = 2 };
+
+typedef struct svsb200_index svsb200_index;
+
+const char* svsb200_last_error(void);
+int svsb200_version(void);
+/* Number of usable CUDA devices (0 if none); fills `sm` with the compute capability*10
+ * of `device` when non-NULL. */
+int svsb200_device_count(void);
+int svsb200_device_sm(int device, int* sm);
+
+/* Replaces: VamanaIndex(graph, data, entry_point, distance, threadpool)
+ *           (include/svs/index/vamana/index.h:364-378) / auto_assemble (:1022-1077).
+ * Copies the host arrays into HBM (the caller keeps ownership of its memory):
+ *   vectors     n rows of `dim` elements of `dtype`, `row_stride_bytes` apart (0 = dense);
+ *               for SQ the rows are the int8/uint8 codes, for LVQ8 see svsb200_lvq8_*.
+ *   graph_rows  the reference's in-memory adjacency: uint32[n][graph_row_len], element 0 =
+ *               out-degree, then the neighbours (include/svs/core/graph/graph.h:103-114);
+ *               graph_row_len = max_degree + 1.
+ *   entry_point the medoid / configured entry point (index.h:312,373).
+ */
+int svsb200_index_create(
+    const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes,
+    const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric,
+    int storage, const float* aux, int device, svsb200_index** out);
+
+int svsb200_index_destroy(svsb200_index* index);
+
+/* Introspection used by the host-side mirror (size()/dimensions()/get_graph_max_degree,
+ * orchestrators/vamana.h:127-275). */
+size_t svsb200_index_size(const svsb200_index* index);
+size_t svsb200_index_dimensions(const svsb200_index* index);
+size_t svsb200_index_max_degree(const svsb200_index* index);
+size_t svsb200_index_device_bytes(const svsb200_index* index);
+int svsb200_index_device(const svsb200_index* index);
+
+/* Replaces: VamanaIndex::search(QueryResultView<I>, queries, VamanaSearchParameters, cancel)
+ *           (include/svs/index/vamana/index.h:564-611) for a whole batch.
+ *   queries      nq x dim, dense row-major, element type `qdtype` (HOST memory);
+ *   window / capacity = SearchBufferConfig (index/vamana/search_buffer.h:39-96); as in
+ *               index.h:590-592, a capacity < k resets both to k;
+ *   use_visited_set = VamanaSearchParameters::search_buffer_visited_set_
+ *               (search_params.h:42); performance-only, results identical;
+ *   out_ids      nq x k ids of `id_bytes` each; out_dists nq x k float (HOST memory).
+ * Rows with fewer than k reachable candidates are padded with id = all-ones and
+ * dist = +/-inf (the reference leaves stale buffer contents there, extensions.h:588-590).
+ * Blocking: returns after the results are in the host buffers.  The H2D copy, the search
+ * kernel and the D2H copy run on `stream` (a cudaStream_t, or NULL for an internal one). */
+int svsb200_search(
+    svsb200_index* index, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+    size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists,
+    void* stream);
+
+/* Same search with every buffer already resident in HBM on the index's device and no
+ * synchronisation: enqueues on `stream` and returns (bench.py's device-resident `value`,
+ * multi-GPU pipelines that feed NCCL directly). */
+int svsb200_search_device(
+    svsb200_index* index, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
+    size_t capacity, int use_visited_set, void* d_out_ids, int id_bytes, float* d_out_dists,
+    void* stream);
+
+/* Work counters of the most recent search on this index, per query (device arrays are
+ * copied to the host buffers; either may be NULL): expanded nodes and distance
+ * evaluations -- the quantities a reference GreedySearchTracker reports
+ * (index/vamana/greedy_search.h:38-42,165).  Used for the algorithmic-bytes roofline.
+ * Counting is off by default; enable it before the search. */
+int svsb200_set_counting(svsb200_index* index, int enabled);
+int svsb200_get_counters(svsb200_index* index, size_t nq, uint32_t* hops, uint32_t* evals);
+/* Duration in milliseconds of the search kernel of the last svsb200_search* call on this
+ * index (CUDA events on the launching stream; synchronises on the stop event). */
+int svsb200_last_kernel_ms(svsb200_index* index, float* ms);
+/* Number of kernels this library launched so far in this process. */
+uint64_t svsb200_launch_count(void);
+
+/* Tuning knobs (performance only; results never change):
+ *   "warps_per_cta", "ctas_per_sm", "rows_in_flight". 0 restores the default. */
+int svsb200_set_option(svsb200_index* index, const char* name, long value);
+
+/* Mode B of SURVEY.md §8e -- merge per-shard top-k lists (after an NCCL all-gather) into a
+ * global top-k with the reference's TotalOrder (distance, then id; lib/neighbor.h:143-155).
+ *   d_ids   [nshards][nq][k] uint64 global ids, d_dists same shape; outputs [nq][k].
+ * metric selects the comparator (L2: smaller is better; IP/cosine: larger is better). */
+int svsb200_merge_topk_device(
+    const uint64_t* d_ids, const float* d_dists, size_t nshards, size_t nq, size_t k, int metric,
+    uint64_t* d_out_ids, float* d_out_dists, int device, void* stream);
+
+/* Exhaustive search used by the harness for ground truth (replaces svs::Flat /
+ * index/flat/flat.h:159 for recall measurement only): top-k of every query against all
+ * `n` base vectors already on the device inside `index`. Distances use the same exact
+ * expression tree as the graph search, ties broken by id. */
+int svsb200_exhaustive_device(
+    svsb200_index* index, const void* d_queries, int qdtype, size_t nq, size_t k,
+    uint64_t* d_out_ids, float* d_out_dists, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVSB200_H */

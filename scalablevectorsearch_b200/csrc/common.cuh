@@ -1,0 +1,79 @@
+// common.cuh -- shared definitions for libsvsb200 (sm_100a only).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/svsb200.h"
+
+namespace svsb200 {
+
+constexpr uint32_t kNoNeighbor = 0xFFFFFFFFu;   // padding of adjacency rows in HBM
+constexpr uint32_t kVisitedBit = 0x80000000u;   // SearchNeighbor::visited packed into the id
+constexpr uint32_t kIdMask = 0x7FFFFFFFu;
+
+// Distance operator of the search kernel.
+//   *F: the reference's fp32 expression tree (generic_simd_op, simd_utils.h:204-252)
+//   *I: exact int32 arithmetic for (int8,int8)/(uint8,uint8) (L2VNNIOp/IPVNNIOp)
+enum Op : int { OP_L2F = 0, OP_IPF = 1, OP_COSF = 2, OP_L2I = 3, OP_IPI = 4, OP_COSI = 5 };
+
+// Everything the search kernel needs; passed by value (__grid_constant__).
+struct SearchParams {
+    // index
+    const void* vectors;       // HBM, row-major, `row_stride` bytes apart (multiple of 16)
+    const uint32_t* graph;     // HBM, uint32[n][gstride], neighbours then kNoNeighbor padding
+    const uint16_t* ref_degree; // HBM, out-degree as the reference stores it (repeats included); counters only
+    uint32_t n;
+    uint32_t dim;
+    uint32_t row_stride;
+    uint32_t gstride;
+    uint32_t entry_point;
+    // distance post-processing
+    int greater;               // comparator std::greater (IP / cosine): keys are negated
+    int sq;                    // rows are scalar-quantised codes
+    float scale, bias, scale_sq;
+    // prepared queries (output of prepare_queries)
+    const float* qf;           // [nq][qstride] fp32 operands of the float tree
+    const uint8_t* qcodes;     // [nq][qstride] int8/uint8 operands of the integer kernels
+    const float* qaux;         // [nq][2]: {a_norm | offset, float(sum x*x)}
+    uint32_t qstride;          // elements; multiple of 16
+    uint32_t nq;
+    // search buffer configuration
+    uint32_t k, window, capacity;
+    uint32_t cap_pad;          // capacity+1 rounded up to 32
+    uint32_t deg_pad;          // gstride rounded up to 32
+    // outputs
+    void* out_ids;
+    int id_bytes;
+    float* out_dists;
+    // bookkeeping
+    unsigned int* work_counter;  // dynamic query scheduler
+    uint32_t* hops;              // optional per-query counters
+    uint32_t* evals;
+};
+
+struct LaunchConfig {
+    int grid;
+    int warps_per_cta;
+    size_t smem_bytes;
+    cudaStream_t stream;
+};
+
+// Per-warp shared-memory footprint of the search kernel (bytes), mirrored on the host.
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad) {
+    // query (fp32 or bytes, reserve fp32) + buffer keys/ids + candidate keys/ids +
+    // survivor keys/pos/ids/final-pos
+    return size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 + size_t(deg_pad) * 16;
+}
+
+// One launcher per (row type, op); defined in search_<type>.cu.
+template <int ROWT> cudaError_t launch_search(int op, const SearchParams& p, const LaunchConfig& cfg, int rows_in_flight);
+
+void count_launch();
+
+}  // namespace svsb200

@@ -1,0 +1,15 @@
+// search_f16.cu -- search-kernel instantiations for f16 base vectors.
+#include "search_kernel.cuh"
+
+namespace svsb200 {
+
+template <> cudaError_t launch_search<SVSB200_F16>(int op, const SearchParams& p, const LaunchConfig& cfg, int nrows) {
+    switch (op) {
+        case OP_L2F: return launch_dims<SVSB200_F16, OP_L2F>(p, cfg, nrows);
+        case OP_IPF: return launch_dims<SVSB200_F16, OP_IPF>(p, cfg, nrows);
+        case OP_COSF: return launch_dims<SVSB200_F16, OP_COSF>(p, cfg, nrows);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace svsb200

@@ -1,0 +1,593 @@
+// search_kernel.cuh -- the Vamana batched greedy search as one persistent sm_100a kernel.
+//
+// Replaces, for a whole query batch (file:line under /root/reference/include/svs):
+//   index/vamana/index.h:564-611        VamanaIndex::search       (thread pool -> grid)
+//   index/vamana/greedy_search.h:124-203 greedy_search            (one warp per query)
+//   index/vamana/search_buffer.h:104-497 SearchBuffer             (sorted buffer in smem)
+//   core/distance/simd_utils.h:204-252   generic_simd_op + L2/IP/Cosine ops (bit-exact)
+//
+// Mapping
+//   * one warp owns one query at a time and pulls query indices from a global counter
+//     (persistent CTAs, grid = SMs x resident CTAs);
+//   * per expanded node the warp reads the adjacency row (coalesced), then evaluates the
+//     neighbours' distances GROUPS rows at a time: a row is owned by G = 16/LPT adjacent
+//     threads, thread t of the group holding logical AVX-512 lanes [LPT*t, LPT*t+LPT) of
+//     every 16-element chunk, so each thread issues 128-bit (f32/f16) loads of its own
+//     row and keeps the reference's 16-lane x 4-accumulator FMA tree entirely in
+//     registers; the 8/4/2/1 reduction is two xor-shuffle levels plus in-thread adds;
+//   * the <= max_degree candidates of a node are then merged into the sorted buffer in one
+//     step.  The merge reproduces the result of the reference's sequential
+//     `for id in neighbours: buffer.insert(...)` exactly: stable order
+//     (new after equal old, adjacency order among equal new), duplicate-id rejection over
+//     the equal-distance run, truncation at capacity, and the best-unvisited cursor.
+#pragma once
+
+#include "common.cuh"
+
+namespace svsb200 {
+
+// ---------------------------------------------------------------------------------------
+// Row access: how one thread fetches its LPT lanes of one 16-element chunk.
+// ---------------------------------------------------------------------------------------
+template <int ROWT> struct Row;
+
+template <> struct Row<SVSB200_F32> {
+    static constexpr int LPT = 4, ESIZE = 4;
+    using raw_t = float4;
+    __device__ static __forceinline__ raw_t load(const char* p) {
+        return __ldg(reinterpret_cast<const float4*>(p));
+    }
+    __device__ static __forceinline__ void cvt(const raw_t& r, float (&y)[4]) {
+        y[0] = r.x; y[1] = r.y; y[2] = r.z; y[3] = r.w;
+    }
+};
+template <> struct Row<SVSB200_F16> {
+    static constexpr int LPT = 8, ESIZE = 2;
+    using raw_t = uint4;
+    __device__ static __forceinline__ raw_t load(const char* p) {
+        return __ldg(reinterpret_cast<const uint4*>(p));
+    }
+    __device__ static __forceinline__ void cvt(const raw_t& r, float (&y)[8]) {
+        // __half2float is exact and honours subnormals, like vcvtph2ps (simd_utils.h:270).
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            __half2 h = *reinterpret_cast<const __half2*>(&w[i]);
+            y[2 * i] = __low2float(h);
+            y[2 * i + 1] = __high2float(h);
+        }
+    }
+};
+template <> struct Row<SVSB200_I8> {
+    static constexpr int LPT = 8, ESIZE = 1;
+    using raw_t = uint2;
+    __device__ static __forceinline__ raw_t load(const char* p) {
+        return __ldg(reinterpret_cast<const uint2*>(p));
+    }
+    __device__ static __forceinline__ void cvt(const raw_t& r, float (&y)[8]) {
+        const uint32_t w[2] = {r.x, r.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            y[i] = float(int(int8_t((w[i >> 2] >> (8 * (i & 3))) & 0xFF)));
+        }
+    }
+};
+template <> struct Row<SVSB200_U8> {
+    static constexpr int LPT = 8, ESIZE = 1;
+    using raw_t = uint2;
+    __device__ static __forceinline__ raw_t load(const char* p) {
+        return __ldg(reinterpret_cast<const uint2*>(p));
+    }
+    __device__ static __forceinline__ void cvt(const raw_t& r, float (&y)[8]) {
+        const uint32_t w[2] = {r.x, r.y};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            y[i] = float((w[i >> 2] >> (8 * (i & 3))) & 0xFF);
+        }
+    }
+};
+
+// One accumulate step of the op (euclidean.h:247-250, inner_product.h:206-208,
+// cosine.h:238-241).  Explicit _rn intrinsics: never contracted, never reordered.
+template <int OP> __device__ __forceinline__ void accumulate(float& s, float& nrm, float x, float y) {
+    if constexpr (OP == OP_L2F) {
+        float c = __fsub_rn(x, y);
+        s = __fmaf_rn(c, c, s);
+    } else {
+        s = __fmaf_rn(x, y, s);
+        if constexpr (OP == OP_COSF) {
+            nrm = __fmaf_rn(y, y, nrm);
+        }
+    }
+}
+
+// _mm512_reduce_add_ps over the 16 logical lanes spread across the G threads of a group.
+template <int LPT> __device__ __forceinline__ float reduce_lanes(float (&s)[LPT]) {
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    if constexpr (LPT == 4) {
+        // lanes L and L+8 live in threads t and t^2, same slot.
+        float v[4], w[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) v[l] = __fadd_rn(__shfl_xor_sync(FULL, s[l], 2), s[l]);
+        // lanes L and L+4 (L<4) live in threads 0 and 1.
+#pragma unroll
+        for (int l = 0; l < 4; ++l) w[l] = __fadd_rn(__shfl_xor_sync(FULL, v[l], 1), v[l]);
+        return __fadd_rn(__fadd_rn(w[0], w[2]), __fadd_rn(w[1], w[3]));
+    } else {
+        static_assert(LPT == 8, "unsupported lane split");
+        float v[8], w[4];
+#pragma unroll
+        for (int l = 0; l < 8; ++l) v[l] = __fadd_rn(__shfl_xor_sync(FULL, s[l], 1), s[l]);
+#pragma unroll
+        for (int l = 0; l < 4; ++l) w[l] = __fadd_rn(v[l + 4], v[l]);
+        return __fadd_rn(__fadd_rn(w[0], w[2]), __fadd_rn(w[1], w[3]));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Float-tree distance of NROWS rows against the query staged in shared memory.
+//   rowp[r]   this thread group's row base pointers (nullptr = inactive slot)
+//   t         thread index inside the group
+// Returns the *raw* reduced sums (op, norm) -- identical in every thread of the group.
+// ---------------------------------------------------------------------------------------
+template <int ROWT, int OP, int DS, int NROWS>
+__device__ __forceinline__ void float_rows(
+    const SearchParams& p, const float* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
+    float (&sum)[NROWS], float (&nrm)[NROWS]) {
+    using R = Row<ROWT>;
+    constexpr int LPT = R::LPT;
+    const int D = DS ? DS : int(p.dim);
+    const bool sqcos = (OP == OP_COSF) && p.sq;
+
+    float s[NROWS][4][LPT];
+    float n[NROWS][4][LPT];
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                s[r][k][l] = 0.0f;
+                n[r][k][l] = 0.0f;
+            }
+
+    const int thread_elem = LPT * t;                 // first element of this thread in a chunk
+    const int nblk = D >> 6;                         // 64-element main blocks
+    int base = 0;                                    // element offset of the current chunk group
+#pragma unroll(DS ? 16 : 1)
+    for (int b = 0; b < nblk; ++b, base += 64) {
+        typename R::raw_t raw[NROWS][4];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (rowp[r]) raw[r][k] = R::load(rowp[r] + size_t(base + 16 * k + thread_elem) * R::ESIZE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float x[LPT];
+#pragma unroll
+            for (int l = 0; l < LPT; l += 4) {
+                float4 qv = *reinterpret_cast<const float4*>(q_s + base + 16 * k + thread_elem + l);
+                x[l] = qv.x; x[l + 1] = qv.y; x[l + 2] = qv.z; x[l + 3] = qv.w;
+            }
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r) {
+                if (!rowp[r]) continue;
+                float y[LPT];
+                R::cvt(raw[r][k], y);
+#pragma unroll
+                for (int l = 0; l < LPT; ++l) {
+                    float yy = sqcos ? __fadd_rn(__fmul_rn(p.scale, y[l]), p.bias) : y[l];
+                    accumulate<OP>(s[r][k][l], n[r][k][l], x[l], yy);
+                }
+            }
+        }
+    }
+    if (nblk > 0) {
+        // s0 = (s0 + s1) + (s2 + s3)   (simd_utils.h:238)
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                s[r][0][l] = __fadd_rn(__fadd_rn(s[r][0][l], s[r][1][l]), __fadd_rn(s[r][2][l], s[r][3][l]));
+                if constexpr (OP == OP_COSF)
+                    n[r][0][l] = __fadd_rn(__fadd_rn(n[r][0][l], n[r][1][l]), __fadd_rn(n[r][2][l], n[r][3][l]));
+            }
+    }
+    // Up to three full 16-wide chunks plus one masked remainder, all into s0, in order
+    // (simd_utils.h:242-250).  Elements >= D are inactive lanes: the accumulator is kept.
+    if (base < D) {
+        typename R::raw_t raw[NROWS][4];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (rowp[r] && base + 16 * k + thread_elem < D)
+                    raw[r][k] = R::load(rowp[r] + size_t(base + 16 * k + thread_elem) * R::ESIZE);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int e0 = base + 16 * k + thread_elem;
+            if (e0 < D) {
+                float x[LPT];
+#pragma unroll
+                for (int l = 0; l < LPT; l += 4) {
+                    float4 qv = *reinterpret_cast<const float4*>(q_s + e0 + l);
+                    x[l] = qv.x; x[l + 1] = qv.y; x[l + 2] = qv.z; x[l + 3] = qv.w;
+                }
+#pragma unroll
+                for (int r = 0; r < NROWS; ++r) {
+                    if (!rowp[r]) continue;
+                    float y[LPT];
+                    R::cvt(raw[r][k], y);
+#pragma unroll
+                    for (int l = 0; l < LPT; ++l) {
+                        if (e0 + l < D) {
+                            float yy = sqcos ? __fadd_rn(__fmul_rn(p.scale, y[l]), p.bias) : y[l];
+                            accumulate<OP>(s[r][0][l], n[r][0][l], x[l], yy);
+                        }
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+        sum[r] = reduce_lanes<LPT>(s[r][0]);
+        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(n[r][0]);
+    }
+}
+
+// Exact integer sums for (int8,int8)/(uint8,uint8): groups of 4 threads, 16-byte loads,
+// dp4a.  Order-free (integer), so any lane split is bit-exact.
+template <int ROWT, int NROWS>
+__device__ __forceinline__ void int_rows(
+    const SearchParams& p, const uint8_t* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
+    int (&xy)[NROWS], int (&yy)[NROWS]) {
+    const int nvec = (int(p.dim) + 15) >> 4;   // rows and query are zero-padded to 16 bytes
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+        xy[r] = 0;
+        yy[r] = 0;
+    }
+    for (int v = t; v < nvec; v += 4) {
+        uint4 qv = *reinterpret_cast<const uint4*>(q_s + 16 * v);
+        const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+            if (!rowp[r]) continue;
+            uint4 rv = __ldg(reinterpret_cast<const uint4*>(rowp[r] + 16 * v));
+            const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                if constexpr (ROWT == SVSB200_I8) {
+                    xy[r] = __dp4a(int(qw[i]), int(rw[i]), xy[r]);
+                    yy[r] = __dp4a(int(rw[i]), int(rw[i]), yy[r]);
+                } else {
+                    xy[r] = int(__dp4a(qw[i], rw[i], unsigned(xy[r])));
+                    yy[r] = int(__dp4a(rw[i], rw[i], unsigned(yy[r])));
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+        xy[r] += __shfl_xor_sync(0xFFFFFFFFu, xy[r], 2);
+        xy[r] += __shfl_xor_sync(0xFFFFFFFFu, xy[r], 1);
+        yy[r] += __shfl_xor_sync(0xFFFFFFFFu, yy[r], 2);
+        yy[r] += __shfl_xor_sync(0xFFFFFFFFu, yy[r], 1);
+    }
+}
+
+// Final scalar expression of each distance functor (after the reduction).
+template <int OP>
+__device__ __forceinline__ float finish_distance(const SearchParams& p, float sum, float nrm, int ixy, int iyy,
+                                                 float aux0, float aux1) {
+    if constexpr (OP == OP_L2F) {
+        return sum;
+    } else if constexpr (OP == OP_IPF) {
+        // InnerProductCompressed::compute: scale * ip + offset (scalar.h:139-141).
+        return p.sq ? __fadd_rn(__fmul_rn(p.scale, sum), aux0) : sum;
+    } else if constexpr (OP == OP_COSF) {
+        // cosine.h:334-335: sum / (sqrt(norm) * a_norm)
+        return __fdiv_rn(sum, __fmul_rn(__fsqrt_rn(nrm), aux0));
+    } else if constexpr (OP == OP_L2I) {
+        // sum (x-y)^2 = xx - 2xy + yy, exact in int32; EuclideanCompressed scales by
+        // scale^2 (scalar.h:92-93).
+        int l2 = __float_as_int(aux1) + iyy - 2 * ixy;   // aux1 carries the int32 bits of sum x*x
+        float f = float(l2);
+        return p.sq ? __fmul_rn(p.scale_sq, f) : f;
+    } else if constexpr (OP == OP_IPI) {
+        return float(ixy);
+    } else {
+        // cosine.h:292-296: float(sum) / (a_norm * sqrt(float(bnorm)))
+        return __fdiv_rn(float(ixy), __fmul_rn(aux0, __fsqrt_rn(float(iyy))));
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// The kernel.
+// ---------------------------------------------------------------------------------------
+template <int ROWT, int OP, int DS, int NROWS>
+__global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constant__ SearchParams p) {
+    constexpr bool kInt = (OP >= OP_L2I);
+    constexpr int G = kInt ? 4 : 16 / Row<ROWT>::LPT;     // threads per row
+    constexpr int GROUPS = 32 / G;                        // rows per warp per slot
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int g = lane / G;      // group inside the warp
+    const int t = lane % G;      // thread inside the group
+
+    unsigned char* wbase = smem_raw + size_t(warp) * warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad);
+    float* q_s = reinterpret_cast<float*>(wbase);
+    float* bkey = q_s + p.qstride;                                      // [cap_pad] sort keys
+    uint32_t* bid = reinterpret_cast<uint32_t*>(bkey + p.cap_pad);      // [cap_pad] id | visited
+    float* ckey = reinterpret_cast<float*>(bid + p.cap_pad);            // [deg_pad] candidate keys
+    uint32_t* cid = reinterpret_cast<uint32_t*>(ckey + p.deg_pad);      // [deg_pad] candidate ids
+    float* skey = reinterpret_cast<float*>(cid + p.deg_pad);            // [deg_pad] survivors
+    uint32_t* spos = reinterpret_cast<uint32_t*>(skey + p.deg_pad);
+    uint32_t* sid = spos + p.deg_pad;
+    uint32_t* sfp = sid + p.deg_pad;
+
+    const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
+    const uint32_t C = p.capacity, W = p.window;
+    const uint32_t hibit = 1u << (31 - __clz(int(C)));
+    const char* vectors = reinterpret_cast<const char*>(p.vectors);
+
+    for (;;) {
+        uint32_t q = 0;
+        if (lane == 0) q = atomicAdd(p.work_counter, 1u);
+        q = __shfl_sync(FULL, q, 0);
+        if (q >= p.nq) break;
+
+        // ---- stage the prepared query (maybe_fix_argument already applied) ----
+        if constexpr (kInt) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.qcodes + size_t(q) * p.qstride);
+            uint32_t* dst = reinterpret_cast<uint32_t*>(q_s);
+            for (uint32_t i = lane; i < p.qstride / 4; i += 32) dst[i] = src[i];
+        } else {
+            const float* src = p.qf + size_t(q) * p.qstride;
+            for (uint32_t i = lane; i < p.qstride; i += 32) q_s[i] = src[i];
+        }
+        const float aux0 = p.qaux[2 * size_t(q)], aux1 = p.qaux[2 * size_t(q) + 1];
+        __syncwarp();
+
+        // Distance of up to NROWS rows per group; thread t==0 of each group publishes keys.
+        auto eval_rows = [&](const uint32_t (&ids)[NROWS], const bool (&on)[NROWS], float (&key)[NROWS]) {
+            const char* rowp[NROWS];
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r) rowp[r] = on[r] ? vectors + size_t(ids[r]) * p.row_stride : nullptr;
+            float sum[NROWS], nrm[NROWS];
+            int ixy[NROWS], iyy[NROWS];
+            if constexpr (kInt) {
+                int_rows<ROWT, NROWS>(p, reinterpret_cast<const uint8_t*>(q_s), rowp, t, ixy, iyy);
+            } else {
+                float_rows<ROWT, OP, DS, NROWS>(p, q_s, rowp, t, sum, nrm);
+            }
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r) {
+                float d = finish_distance<OP>(p, kInt ? 0.f : sum[r], (OP == OP_COSF) ? nrm[r] : 0.f,
+                                              kInt ? ixy[r] : 0, kInt ? iyy[r] : 0, aux0, aux1);
+                key[r] = __fmul_rn(d, ksign);
+            }
+        };
+
+        // ---- EntryPointInitializer (greedy_search.h:62-94): clear, push entry point ----
+        uint32_t size = 1, cursor = 0, n_hops = 0, n_evals = 1;
+        {
+            uint32_t ids[NROWS];
+            bool on[NROWS];
+            float key[NROWS];
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r) {
+                ids[r] = p.entry_point;
+                on[r] = (r == 0);
+            }
+            eval_rows(ids, on, key);
+            if (lane == 0) {
+                bkey[0] = key[0];
+                bid[0] = p.entry_point;
+            }
+        }
+        __syncwarp();
+
+        // ---- main loop: while (!buffer.done()) (greedy_search.h:153) ----
+        for (;;) {
+            // buffer.next(): first unvisited entry inside min(size, window)
+            const uint32_t upper = min(size, W);
+            uint32_t pos = cursor;
+            bool found = false;
+            while (pos < upper) {
+                uint32_t j = pos + lane;
+                bool unv = (j < upper) && !(bid[j] & kVisitedBit);
+                unsigned m = __ballot_sync(FULL, unv);
+                if (m) {
+                    pos += __ffs(m) - 1;
+                    found = true;
+                    break;
+                }
+                pos += 32;
+            }
+            if (!found) break;   // done()
+            const uint32_t node = bid[pos];
+            __syncwarp();
+            if (lane == 0) bid[pos] = node | kVisitedBit;
+            cursor = pos + 1;
+
+            // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding
+            const uint32_t* grow = p.graph + size_t(node) * p.gstride;
+            uint32_t deg = 0;
+            for (uint32_t j0 = 0; j0 < p.gstride; j0 += 32) {
+                uint32_t j = j0 + lane;
+                uint32_t nb = (j < p.gstride) ? __ldg(grow + j) : kNoNeighbor;
+                cid[j] = nb;
+                deg += __popc(__ballot_sync(FULL, nb != kNoNeighbor));
+            }
+            __syncwarp();
+            ++n_hops;
+            // tracker.visited(node, neighbors.size()) (greedy_search.h:165) counts the row as
+            // the reference stores it, i.e. including the repeated ids removed at upload.
+            n_evals += p.hops ? uint32_t(__ldg(p.ref_degree + node)) : deg;
+
+            // neighbour expansion: distance of every neighbour (greedy_search.h:190-201)
+            for (uint32_t base = 0; base < deg; base += NROWS * GROUPS) {
+                uint32_t ids[NROWS];
+                bool on[NROWS];
+                float key[NROWS];
+#pragma unroll
+                for (int r = 0; r < NROWS; ++r) {
+                    uint32_t idx = base + r * GROUPS + g;
+                    on[r] = idx < deg;
+                    ids[r] = on[r] ? cid[idx] : 0;
+                }
+                eval_rows(ids, on, key);
+                if (t == 0) {
+#pragma unroll
+                    for (int r = 0; r < NROWS; ++r)
+                        if (on[r]) ckey[base + r * GROUPS + g] = key[r];
+                }
+            }
+            __syncwarp();
+
+            // ---- merge the candidates into the sorted buffer (== sequential insert) ----
+            const bool full = (size == C);
+            const float backkey = bkey[size - 1];
+            uint32_t S = 0, minpos = 0xFFFFFFFFu;
+            for (uint32_t r0 = 0; r0 < deg; r0 += 32) {
+                const uint32_t r = r0 + lane;
+                const bool valid = r < deg;
+                const float d = valid ? ckey[r] : 0.0f;
+                const uint32_t id = valid ? cid[r] : 0;
+                // can_skip (search_buffer.h:342-344): full && cmp(back, d)
+                bool surv = valid && !(full && backkey < d);
+                uint32_t ipos = 0;
+                if (__any_sync(FULL, surv)) {
+                    // lower_bound with !cmp(d, other) (search_buffer.h:364-371): number of
+                    // entries that are better than or equal to d.
+                    for (uint32_t step = hibit; step; step >>= 1) {
+                        uint32_t j = ipos + step;
+                        if (surv && j <= size && !(d < bkey[j - 1])) ipos = j;
+                    }
+                    // duplicate-id scan over the equal-key run (search_buffer.h:380-391)
+                    if (surv) {
+                        uint32_t j = ipos;
+                        while (j > 0) {
+                            --j;
+                            if (bkey[j] < d) break;
+                            if ((bid[j] & kIdMask) == id) {
+                                surv = false;
+                                break;
+                            }
+                        }
+                    }
+                }
+                const unsigned m = __ballot_sync(FULL, surv);
+                if (surv) {
+                    const uint32_t ci = S + __popc(m & ((1u << lane) - 1u));
+                    skey[ci] = d;
+                    spos[ci] = ipos;
+                    sid[ci] = id;
+                    minpos = min(minpos, ipos);
+                }
+                S += __popc(m);
+            }
+            if (S == 0) continue;
+            minpos = __reduce_min_sync(FULL, minpos);
+            __syncwarp();
+
+            // final position of every survivor: insertion point + stable rank among survivors
+            for (uint32_t si = lane; si < S; si += 32) {
+                const float md = skey[si];
+                uint32_t rank = 0;
+                for (uint32_t s = 0; s < S; ++s) {
+                    const float ds = skey[s];
+                    rank += (ds < md) || (!(md < ds) && s < si);
+                }
+                sfp[si] = spos[si] + rank;
+            }
+            // shift the old entries, top chunk first so the move is safe in place
+            if (minpos < size) {
+                const int chunk_lo = int(minpos >> 5);
+                for (int ch = int((size - 1) >> 5); ch >= chunk_lo; --ch) {
+                    const uint32_t j = uint32_t(ch) * 32 + lane;
+                    const bool have = j < size;
+                    const float kk = have ? bkey[j] : 0.0f;
+                    const uint32_t ii = have ? bid[j] : 0;
+                    uint32_t shift = 0;
+                    for (uint32_t s = 0; s < S; ++s) shift += (spos[s] <= j);
+                    __syncwarp();
+                    if (have && shift && j + shift < C) {
+                        bkey[j + shift] = kk;
+                        bid[j + shift] = ii;
+                    }
+                    __syncwarp();
+                }
+            }
+            __syncwarp();
+            for (uint32_t si = lane; si < S; si += 32) {
+                const uint32_t fp = sfp[si];
+                if (fp < C) {
+                    bkey[fp] = skey[si];
+                    bid[fp] = sid[si];
+                }
+            }
+            size = min(size + S, C);
+            cursor = min(cursor, minpos);   // best_unvisited = min(best_unvisited, i) (:401)
+            __syncwarp();
+        }
+
+        // ---- copy the first k entries out (extensions.h:588-590) ----
+        for (uint32_t j = lane; j < p.k; j += 32) {
+            const bool valid = j < size;
+            const uint32_t id = valid ? (bid[j] & kIdMask) : 0xFFFFFFFFu;
+            const float dist = valid ? __fmul_rn(bkey[j], ksign) : (p.greater ? -INFINITY : INFINITY);
+            const size_t o = size_t(q) * p.k + j;
+            if (p.id_bytes == 8)
+                reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) : ~uint64_t(0);
+            else
+                reinterpret_cast<uint32_t*>(p.out_ids)[o] = id;
+            p.out_dists[o] = dist;
+        }
+        if (p.hops && lane == 0) {
+            p.hops[q] = n_hops;
+            p.evals[q] = n_evals;
+        }
+        __syncwarp();
+    }
+}
+
+// Host-side launch helper shared by the per-type translation units.
+template <int ROWT, int OP, int DS, int NROWS>
+cudaError_t launch_one(const SearchParams& p, const LaunchConfig& cfg) {
+    auto kernel = vamana_search_kernel<ROWT, OP, DS, NROWS>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
+    if (err != cudaSuccess) return err;
+    int grid = cfg.grid;
+    if (grid < 0) {
+        // persistent grid: SM count x resident CTAs of this instantiation
+        int resident = 0;
+        err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, cfg.warps_per_cta * 32, cfg.smem_bytes);
+        if (err != cudaSuccess) return err;
+        grid = -grid * (resident > 0 ? resident : 1);
+    }
+    const int needed = int((p.nq + cfg.warps_per_cta - 1) / cfg.warps_per_cta);
+    if (grid > needed) grid = needed;
+    kernel<<<grid, cfg.warps_per_cta * 32, cfg.smem_bytes, cfg.stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int ROWT, int OP> cudaError_t launch_dims(const SearchParams& p, const LaunchConfig& cfg, int nrows) {
+    // Static dimensions get fully unrolled loads (all of a row's loads in flight at once);
+    // everything else takes the dynamic-length path.  Same expression tree either way,
+    // like the reference's static-N vs Dynamic kernels (distance_core.h:31-42).
+    if constexpr (OP < OP_L2I) {
+        if (p.dim == 96) return nrows == 1 ? launch_one<ROWT, OP, 96, 1>(p, cfg) : launch_one<ROWT, OP, 96, 2>(p, cfg);
+        if (p.dim == 128) return nrows == 1 ? launch_one<ROWT, OP, 128, 1>(p, cfg) : launch_one<ROWT, OP, 128, 2>(p, cfg);
+    }
+    return nrows == 1 ? launch_one<ROWT, OP, 0, 1>(p, cfg) : launch_one<ROWT, OP, 0, 2>(p, cfg);
+}
+
+}  // namespace svsb200

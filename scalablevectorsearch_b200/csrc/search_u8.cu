@@ -1,0 +1,18 @@
+// search_u8.cu -- search-kernel instantiations for u8 base vectors.
+#include "search_kernel.cuh"
+
+namespace svsb200 {
+
+template <> cudaError_t launch_search<SVSB200_U8>(int op, const SearchParams& p, const LaunchConfig& cfg, int nrows) {
+    switch (op) {
+        case OP_L2F: return launch_dims<SVSB200_U8, OP_L2F>(p, cfg, nrows);
+        case OP_IPF: return launch_dims<SVSB200_U8, OP_IPF>(p, cfg, nrows);
+        case OP_COSF: return launch_dims<SVSB200_U8, OP_COSF>(p, cfg, nrows);
+        case OP_L2I: return launch_dims<SVSB200_U8, OP_L2I>(p, cfg, nrows);
+        case OP_IPI: return launch_dims<SVSB200_U8, OP_IPI>(p, cfg, nrows);
+        case OP_COSI: return launch_dims<SVSB200_U8, OP_COSI>(p, cfg, nrows);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace svsb200

@@ -1,0 +1,257 @@
+"""Host-side mirror of the reference's Vamana search interface, backed by ``libsvsb200.so``.
+
+Names, argument meaning and error behaviour follow the reference's Python binding of
+``svs::Vamana`` (``/root/reference/bindings/python/src/vamana.cpp:340-348,409-451``,
+``include/svs/python/manager.h:34-58,85-142``, ``src/vamana_common.cpp:88-160``):
+
+    index = Vamana(config_path, GraphLoader(dir), VectorDataLoader(path, DataType.float32),
+                   distance=DistanceType.L2)
+    index.search_window_size = 128
+    I, D = index.search(queries, 10)          # numpy (nq, k) uint64 / float32
+
+Everything that is not batch search (build, save, reconstruct, calibrate ...) stays on the
+reference's CPU code and is out of scope here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import os
+import re
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib, io
+
+
+class DistanceType(enum.IntEnum):
+    """``svs.DistanceType`` (core/distance.h:41-60)."""
+    L2 = 0
+    MIP = 1
+    Cosine = 2
+
+
+class DataType(enum.Enum):
+    """``svs.DataType`` restricted to the element types the search path supports."""
+    float32 = np.dtype(np.float32)
+    float16 = np.dtype(np.float16)
+    int8 = np.dtype(np.int8)
+    uint8 = np.dtype(np.uint8)
+
+
+_DTYPE_CODE = {np.dtype(np.float32): 0, np.dtype(np.float16): 1, np.dtype(np.int8): 2, np.dtype(np.uint8): 3}
+_STORAGE_PLAIN, _STORAGE_SQ = 0, 1
+
+
+@dataclass
+class SearchBufferConfig:
+    """``svs.SearchBufferConfig`` (index/vamana/search_buffer.h:39-96)."""
+    search_window_size: int = 0
+    search_buffer_capacity: int | None = None
+
+    def __post_init__(self):
+        if self.search_buffer_capacity is None:
+            self.search_buffer_capacity = self.search_window_size
+        if self.search_window_size > self.search_buffer_capacity:
+            raise ValueError(
+                f"Improper configuration for search buffer! Effective size ({self.search_window_size}) "
+                f"cannot be less than capacity ({self.search_buffer_capacity}).")
+
+
+@dataclass
+class VamanaSearchParameters:
+    """``svs.VamanaSearchParameters`` (index/vamana/search_params.h:27-128).
+
+    ``prefetch_*`` are accepted for interface parity; the GPU hides latency with warps in
+    flight instead of software prefetch (lib/prefetch.h)."""
+    buffer_config: SearchBufferConfig = field(default_factory=SearchBufferConfig)
+    search_buffer_visited_set: bool = False
+    prefetch_lookahead: int = 4
+    prefetch_step: int = 1
+
+
+@dataclass
+class VectorDataLoader:
+    """``svs.VectorDataLoader``: a ``.svs`` / ``.fvecs`` style file plus its element type."""
+    path: str
+    data_type: DataType = DataType.float32
+    dims: int = 0
+
+    def load(self) -> np.ndarray:
+        dt = self.data_type.value
+        ext = os.path.splitext(self.path)[1]
+        if os.path.isdir(self.path):
+            path = os.path.join(self.path, "data_0.svs") if os.path.exists(os.path.join(self.path, "data_0.svs")) \
+                else self.path
+            return io.read_svs(path, dt)
+        if ext in (".fvecs", ".ivecs", ".bvecs", ".hvecs"):
+            return io.read_vecs(self.path, dt)
+        return io.read_svs(self.path, dt)
+
+
+@dataclass
+class GraphLoader:
+    """``svs.GraphLoader``: a native graph file (or the directory holding ``graph_0.svs``)."""
+    path: str
+
+    def load(self) -> np.ndarray:
+        path = self.path
+        if os.path.isdir(path):
+            path = os.path.join(path, "graph_0.svs")
+        return io.read_graph(path)
+
+
+def _read_entry_point(config_path: str) -> int:
+    """``entry_point`` of a ``vamana_index_parameters`` TOML (index/vamana/index.h:53-178)."""
+    path = config_path
+    if os.path.isdir(path):
+        path = os.path.join(path, "svs_config.toml")
+    with open(path) as f:
+        m = re.search(r"^\s*entry_point\s*=\s*(\d+)", f.read(), re.M)
+    if not m:
+        raise ValueError(f"{path}: no entry_point")
+    return int(m.group(1))
+
+
+class Vamana:
+    """GPU-backed static Vamana index exposing the reference's search surface."""
+
+    def __init__(self, config_path, graph_loader, data_loader, distance: DistanceType = DistanceType.L2,
+                 query_type: DataType = DataType.float32, enforce_dims: bool = False, num_threads: int = 1,
+                 device: int = 0):
+        graph = graph_loader.load() if hasattr(graph_loader, "load") else np.asarray(graph_loader)
+        data = data_loader.load() if hasattr(data_loader, "load") else np.asarray(data_loader)
+        self._init(data, graph, _read_entry_point(config_path), distance, device, num_threads)
+
+    @classmethod
+    def from_arrays(cls, data: np.ndarray, graph: np.ndarray, entry_point: int,
+                    distance: DistanceType = DistanceType.L2, device: int = 0, sq: tuple | None = None,
+                    num_threads: int = 1) -> "Vamana":
+        """Assemble from in-memory parts: ``VamanaIndex(graph, data, entry_point, distance, threads)``
+        (index/vamana/index.h:364-378).  ``graph`` is ``uint32[n][max_degree+1]``, degree first.
+        ``sq=(scale, bias)`` marks ``data`` as scalar-quantised int8/uint8 codes."""
+        self = cls.__new__(cls)
+        self._init(data, graph, entry_point, distance, device, num_threads, sq)
+        return self
+
+    def _init(self, data, graph, entry_point, distance, device, num_threads, sq=None):
+        data = np.ascontiguousarray(data)
+        graph = np.ascontiguousarray(graph, dtype=np.uint32)
+        if data.ndim != 2 or graph.ndim != 2:
+            raise ValueError("data and graph must be 2-D")
+        if data.dtype not in _DTYPE_CODE:
+            raise TypeError(f"unsupported data type {data.dtype}")
+        if graph.shape[0] != data.shape[0]:
+            raise ValueError("Wrong sizes!")  # index/vamana/index.h:417-419
+        self._lib = _lib.lib()
+        self._distance = DistanceType(distance)
+        self._dtype = data.dtype
+        self._params = VamanaSearchParameters()
+        self._num_threads = int(num_threads)
+        handle = C.c_void_p()
+        aux = None
+        storage = _STORAGE_PLAIN
+        if sq is not None:
+            aux = (C.c_float * 2)(float(sq[0]), float(sq[1]))
+            storage = _STORAGE_SQ
+        _lib.check(self._lib.svsb200_index_create(
+            data.ctypes.data, _DTYPE_CODE[data.dtype], data.shape[0], data.shape[1], 0, graph.ctypes.data,
+            graph.shape[1], int(entry_point), int(self._distance), storage,
+            C.cast(aux, C.c_void_p) if aux is not None else None, int(device), C.byref(handle)))
+        self._h = handle
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.svsb200_index_destroy(h)
+            self._h = None
+
+    # ---- properties (bindings/python/include/svs/python/manager.h:85-110) -------------
+    @property
+    def size(self) -> int:
+        return self._lib.svsb200_index_size(self._h)
+
+    @property
+    def dimensions(self) -> int:
+        return self._lib.svsb200_index_dimensions(self._h)
+
+    @property
+    def graph_max_degree(self) -> int:
+        return self._lib.svsb200_index_max_degree(self._h)
+
+    @property
+    def num_threads(self) -> int:
+        """Kept for interface parity: the reference's thread pool is replaced by the grid."""
+        return self._num_threads
+
+    @num_threads.setter
+    def num_threads(self, n: int):
+        self._num_threads = int(n)
+
+    @property
+    def search_parameters(self) -> VamanaSearchParameters:
+        return self._params
+
+    @search_parameters.setter
+    def search_parameters(self, p: VamanaSearchParameters):
+        self._params = p
+
+    @property
+    def search_window_size(self) -> int:
+        return self._params.buffer_config.search_window_size
+
+    @search_window_size.setter
+    def search_window_size(self, w: int):
+        # orchestrators/vamana.h set_search_window_size: window == capacity
+        self._params.buffer_config = SearchBufferConfig(int(w))
+
+    @property
+    def device_bytes(self) -> int:
+        return self._lib.svsb200_index_device_bytes(self._h)
+
+    # ---- search ------------------------------------------------------------------------
+    def search(self, queries: np.ndarray, n_neighbors: int):
+        """``svs.Vamana.search(queries, n_neighbors)`` -> (ids uint64 [nq,k], distances float32 [nq,k])."""
+        q = np.ascontiguousarray(queries)
+        if q.ndim != 2:
+            raise ValueError("queries must be a 2-D array")
+        if q.dtype not in _DTYPE_CODE:
+            raise TypeError(f"unsupported query type {q.dtype}")
+        if q.shape[1] != self.dimensions:
+            raise ValueError(f"Query has dimension {q.shape[1]}, index has {self.dimensions}")
+        nq, k = q.shape[0], int(n_neighbors)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        cfg = self._params.buffer_config
+        _lib.check(self._lib.svsb200_search(
+            self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k, cfg.search_window_size, cfg.search_buffer_capacity,
+            int(self._params.search_buffer_visited_set), ids.ctypes.data, 8, dists.ctypes.data, None))
+        return ids, dists
+
+    def search_device(self, d_queries: int, qdtype: np.dtype, nq: int, n_neighbors: int, d_ids: int, d_dists: int,
+                      stream: int = 0, id_bytes: int = 8):
+        """Enqueue a search over device-resident buffers (raw pointers, e.g. ``tensor.data_ptr()``)."""
+        cfg = self._params.buffer_config
+        _lib.check(self._lib.svsb200_search_device(
+            self._h, d_queries, _DTYPE_CODE[np.dtype(qdtype)], nq, int(n_neighbors), cfg.search_window_size,
+            cfg.search_buffer_capacity, int(self._params.search_buffer_visited_set), d_ids, id_bytes, d_dists,
+            stream or None))
+
+    # ---- instrumentation ---------------------------------------------------------------
+    def set_counting(self, enabled: bool):
+        _lib.check(self._lib.svsb200_set_counting(self._h, int(enabled)))
+
+    def counters(self, nq: int):
+        hops = np.empty(nq, dtype=np.uint32)
+        evals = np.empty(nq, dtype=np.uint32)
+        _lib.check(self._lib.svsb200_get_counters(self._h, nq, hops.ctypes.data, evals.ctypes.data))
+        return hops, evals
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        _lib.check(self._lib.svsb200_last_kernel_ms(self._h, C.byref(ms)))
+        return float(ms.value)
+
+    def set_option(self, name: str, value: int):
+        _lib.check(self._lib.svsb200_set_option(self._h, name.encode(), int(value)))
