@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- QPS of the Vamana batched search (BASELINE.json metric) on B200, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1], the configuration the metric is quoted on): synthetic 1M x 96-d
+float32, L2, Vamana search_window=128, batch = 10k queries, k = 10; graph built once per box by the
+reference's own CPU builder (oracle/_ref, R=64, window 128, alpha 1.2) and cached under /tmp.
+A "step" = one full pass of the hot path over the 10k-query batch.
+
+Lines printed (rank 0 only):
+  value     whole-job QPS with queries/results resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the C ABI with HOST buffers (pinned), H2D + D2H inside the timed region
+  roofline  algorithmic HBM bytes of the search kernel / its CUDA-event duration vs MEASURED_PEAKS.json
+  cpu_baseline  the reference's own AVX-512 CPU path (oracle/_ref) on this box's host cores
+`--impl reference` times that CPU path alone under the same metric/config.
+"""
+import argparse
+import hashlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: n, dim, dtype, metric, nq, k, window, max_degree, build window
+    "c2-1Mx96-f32-L2-w128": dict(n=1_000_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
+                                 max_degree=64, build_window=128, alpha=1.2),
+    "tiny-100kx96-f32-L2-w128": dict(n=100_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
+                                     max_degree=64, build_window=128, alpha=1.2),
+}
+FALLBACK_HBM_GBS = 6650.0   # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def effective_cpus():
+    """Host cores this process may actually use: min(os.cpu_count, affinity mask, cgroup CPU quota).  On the
+    GPU boxes the container sees 128 logical CPUs but `cpu.max` grants 16; the reference's spin-waiting
+    thread pool collapses when oversubscribed, so its arm is run at the granted count."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ------------------------------------------------------------------------------------------------
+# workload: data + graph (cached per box under /tmp, rank 0 builds)
+# ------------------------------------------------------------------------------------------------
+def load_workload(name, rank, world, barrier):
+    from scalablevectorsearch_b200.synthetic import clustered_unit_vectors
+    w = WORKLOADS[name]
+    t0 = time.time()
+    base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
+    key = hashlib.sha1(json.dumps(w, sort_keys=True).encode()).hexdigest()[:12]
+    cache = os.path.join(os.environ.get("SVSB200_CACHE", "/tmp/svsb200_cache"), f"graph_{name}_{key}.npy")
+    if rank == 0 and not os.path.exists(cache):
+        from oracle.bindings import RefLib   # checker/baseline infrastructure: builds the graph only
+        if not RefLib.available():
+            raise SystemExit("oracle/_ref/libsvsref.so is missing: run `python -c 'import __graft_entry__ as g; "
+                             "g.build()'` where /root/reference exists (the graph comes from the reference builder)")
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        t1 = time.time()
+        graph, ep = RefLib().build(base, w["metric"], w["max_degree"], w["build_window"], alpha=w["alpha"],
+                                   threads=effective_cpus())
+        log(f"reference auto_build n={w['n']} R={w['max_degree']} on {effective_cpus()} threads: {time.time() - t1:.1f} s, "
+            f"avg degree {graph[:, 0].mean():.1f}")
+        tmp = cache + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            np.save(f, np.concatenate([np.array([[ep] + [0] * w["max_degree"]], dtype=np.uint32), graph]))
+        os.replace(tmp, cache)
+    barrier()
+    blob = np.load(cache, mmap_mode="r")
+    ep, graph = int(blob[0, 0]), np.ascontiguousarray(blob[1:])
+    log(f"rank {rank}: workload {name} ready in {time.time() - t0:.1f} s (entry point {ep})")
+    return w, base, queries, graph, ep
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        self.gpu, self.rows, self.proc = gpu, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].startswith("Active") for r in self.rows if len(r) >= 7)]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(sm)}
+
+
+def algorithmic_bytes(hops, evals, rows_read, w, row_bytes, qbytes):
+    """SURVEY.md §8(d) per query: sum_hops 4*(1+deg) + rows * row_bytes + D*sizeof(Tq) + k*8.
+    `evals` = entry points + sum of out-degrees and `hops` = expanded nodes (the counts a reference
+    GreedySearchTracker reports).  `rows_read` is the number of base-vector rows charged: `evals` for the
+    reference-equivalent figure (the CPU path re-reads every neighbour: visited set off by default), or the
+    kernel's own `fetched` counter (rows that pass its exact visited filter) for the bytes the kernel must move."""
+    hops, evals, rows_read = hops.astype(np.float64), evals.astype(np.float64), rows_read.astype(np.float64)
+    per_query = 4.0 * (hops + (evals - 1.0)) + rows_read * row_bytes + qbytes + w["k"] * 8.0
+    return float(per_query.sum()), float(per_query.mean())
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm (CPU): the reference's own AVX-512 path via oracle/_ref
+# ------------------------------------------------------------------------------------------------
+def time_reference(w, base, queries, graph, ep, steps, warmup, threads):
+    from oracle.bindings import RefLib
+    ref = RefLib()
+    idx = ref.index(base, graph, ep, w["metric"], threads=threads)
+    for _ in range(warmup):
+        idx.search(queries, w["k"], w["window"], w["window"])
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ids, dists = idx.search(queries, w["k"], w["window"], w["window"])
+        times.append(time.perf_counter() - t0)
+    return times, ids, dists, ref
+
+
+def run_reference(args):
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    w, base, queries, graph, ep = load_workload(args.workload, 0, 1, lambda: None)
+    threads = effective_cpus()
+    times, _, _, ref = time_reference(w, base, queries, graph, ep, args.steps, args.warmup, threads)
+    total = sum(times)
+    qps = w["nq"] * len(times) / total
+    line = {
+        "impl": "reference", "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.workload, w, graph),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
+                         "sample": f"full {w['nq']}-query batch x {len(times)} steps, {threads} threads = container CPU quota "
+                                   f"(os.cpu_count()={os.cpu_count()}), "
+                                   f"avx512={ref.avx512()}"},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(name, w, graph):
+    return {"workload": name, "n": w["n"], "dim": w["dim"], "base_dtype": w["dtype"], "distance": w["metric"],
+            "batch": w["nq"], "k": w["k"], "search_window": w["window"], "graph_max_degree": w["max_degree"],
+            "graph_avg_degree": round(float(graph[:, 0].mean()), 2),
+            "l2_policy": "index (vectors+graph) is several times larger than the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm (GPU)
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from scalablevectorsearch_b200 import DistanceType, SearchBufferConfig, Vamana, _lib
+    from scalablevectorsearch_b200.multi_gpu import ReplicatedSearch, balance, cuda_local_search
+
+    rank, local_rank, world = dist_env()
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+
+    w, base, queries, graph, ep = load_workload(args.workload, rank, world, barrier)
+    if args.window:
+        w = dict(w, window=args.window)
+    metric = {"l2": DistanceType.L2, "ip": DistanceType.MIP, "cosine": DistanceType.Cosine}[w["metric"]]
+    index = Vamana.from_arrays(base, graph, ep, metric, device=local_rank)
+    index.search_parameters.buffer_config = SearchBufferConfig(w["window"])
+    for opt in ("warps_per_cta", "ctas_per_sm", "rows_in_flight"):
+        if getattr(args, opt):
+            index.set_option(opt, getattr(args, opt))
+    if args.filter_slots >= 0:
+        index.set_option("visited_filter_slots", args.filter_slots)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        index.set_option(name, int(val))
+    lib = _lib.lib()
+    nq, k = w["nq"], w["k"]
+    q_host = torch.from_numpy(queries).pin_memory()
+    q_dev = q_host.to(dev, non_blocking=True)
+    searcher = ReplicatedSearch(cuda_local_search(index))
+    lo, hi = balance(nq, world, rank)
+
+    def step_device():
+        return searcher.search(q_dev, k)
+
+    # ---- per-query work counters (reference tracker equivalents) for the roofline ----
+    index.set_counting(True)
+    ids_all, d_all = step_device()
+    torch.cuda.synchronize()
+    hops, evals = index.counters(hi - lo)
+    fetched = index.fetched(hi - lo)
+    index.set_counting(False)
+    row_bytes = w["dim"] * base.dtype.itemsize
+    qb = w["dim"] * queries.dtype.itemsize
+    shard_bytes, bytes_per_query = algorithmic_bytes(hops, evals, fetched, w, row_bytes, qb)
+    _, ref_bytes_per_query = algorithmic_bytes(hops, evals, evals, w, row_bytes, qb)
+
+    # ---- device-resident timing: W warm-ups, K timed steps, CUDA events, max over ranks ----
+    for _ in range(max(args.warmup, 3) - 1):
+        step_device()
+    torch.cuda.synchronize()
+    barrier()
+    launches0 = lib.svsb200_launch_count()
+    kernel_ms = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            ids_all, d_all = step_device()
+            if args.steps <= 64:
+                pass
+        stop.record()
+        torch.cuda.synchronize()
+    barrier()
+    launches = lib.svsb200_launch_count() - launches0
+    elapsed_ms = start.elapsed_time(stop)
+    # search-kernel duration: CUDA events recorded by the library around the kernel on the same stream
+    for _ in range(3):
+        step_device()
+        torch.cuda.synchronize()
+        kernel_ms.append(index.last_kernel_ms())
+    t = torch.tensor([elapsed_ms, float(np.mean(kernel_ms)), shard_bytes], dtype=torch.float64, device=dev)
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        elapsed_ms, kern_ms, total_bytes = float(tmax[0]), float(tmax[1]), float(tsum[2])
+    else:
+        elapsed_ms, kern_ms, total_bytes = float(t[0]), float(t[1]), float(t[2])
+    qps = nq * args.steps / (elapsed_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (pinned): H2D + search + D2H per step ----
+    out_ids = torch.empty((hi - lo, k), dtype=torch.int64).pin_memory()
+    out_d = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
+    q_shard = q_host[lo:hi]
+    cfg = index.search_parameters.buffer_config
+
+    def step_e2e():
+        _lib.check(lib.svsb200_search(index._h, q_shard.data_ptr(), 0, hi - lo, k, cfg.search_window_size,
+                                      cfg.search_buffer_capacity, 0, out_ids.data_ptr(), 8, out_d.data_ptr(), None))
+
+    for _ in range(3):
+        step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_e2e()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = nq * args.steps / float(te[0])
+    same = bool(np.array_equal(out_ids.numpy(), ids_all[lo:hi].cpu().numpy()))
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+        achieved = total_bytes / (kern_ms * 1e-3) / 1e9 / world   # per-GPU GB/s of the search kernel
+        # recall@10 on a sample against exact brute force (torch matmul: harness only)
+        sample = min(1000, nq)
+        xb = torch.from_numpy(base).to(dev)
+        qs = q_dev[:sample]
+        d2 = (xb * xb).sum(1)[None, :] - 2.0 * qs @ xb.T
+        gt = d2.topk(k, largest=False).indices.cpu().numpy()
+        got = ids_all[:sample].cpu().numpy()
+        recall = float(np.mean([len(set(got[i]) & set(gt[i])) for i in range(sample)])) / k
+        del xb, d2
+
+        cpu = None
+        if not args.no_cpu_baseline:
+            try:
+                threads = effective_cpus()
+                times, ref_ids, _, ref = time_reference(w, base, queries, graph, ep, 5, 1, threads)
+                cpu_qps = nq / min(times)
+                ids_equal = bool(np.array_equal(ref_ids, ids_all.cpu().numpy().astype(np.uint64)))
+                cpu = {"value": nq * len(times) / sum(times), "best": cpu_qps, "unit": "queries/s", "cores": threads,
+                       "kind": "reference",
+                       "sample": f"reference AVX-512 path (oracle/_ref, avx512={ref.avx512()}), full {nq}-query batch, "
+                                 f"1 warm-up + 5 timed searches on {threads} threads = the container's CPU quota "
+                                 f"(os.cpu_count()={os.cpu_count()})",
+                       "ids_identical_to_gpu": ids_equal}
+            except Exception as e:   # noqa: BLE001
+                cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        line = {
+            "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": dict(workload_config(args.workload, w, graph), recall_at_10=round(recall, 4),
+                           parallelism=f"replicas x{world}, query shards, NCCL all-gather of top-k"),
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * w["dim"] * 4),
+                    "d2h_bytes_per_step": int(nq * k * 12), "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "vamana_search_kernel",
+                         "kernel_ms": kern_ms, "algorithmic_bytes_per_query": bytes_per_query,
+                         "reference_equivalent_bytes_per_query": ref_bytes_per_query,
+                         "hops_per_query": float(hops.mean()), "evals_per_query": float(evals.mean()),
+                         "rows_fetched_per_query": float(fetched.mean()),
+                         "note": "achieved = (adjacency rows + base-vector rows the kernel reads after its exact "
+                                 "visited filter + query + results) / kernel time; reference_equivalent counts "
+                                 "every neighbour evaluation of the CPU path (visited set off)"},
+            "cpu_baseline": cpu,
+            "clocks": clocks.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--workload", default=os.environ.get("SVSB200_WORKLOAD", "c2-1Mx96-f32-L2-w128"),
+                    choices=sorted(WORKLOADS))
+    ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--warps-per-cta", dest="warps_per_cta", type=int, default=0)
+    ap.add_argument("--ctas-per-sm", dest="ctas_per_sm", type=int, default=0)
+    ap.add_argument("--rows-in-flight", dest="rows_in_flight", type=int, default=0)
+    ap.add_argument("--filter-slots", dest="filter_slots", type=int, default=-1)
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (svsb200_set_option)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--weak", action="store_true", help="(reserved) per-GPU batch fixed as N grows")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

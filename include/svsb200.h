@@ -85,7 +85,8 @@ int svsb200_index_device(const svsb200_index* index);
  * Rows with fewer than k reachable candidates are padded with id = all-ones and
  * dist = +/-inf (the reference leaves stale buffer contents there, extensions.h:588-590).
  * Blocking: returns after the results are in the host buffers.  The H2D copy, the search
- * kernel and the D2H copy run on `stream` (a cudaStream_t, or NULL for an internal one). */
+ * kernel and the D2H copy run on `stream` (a cudaStream_t; NULL selects the index's own
+ * non-blocking stream -- pass cudaStreamLegacy / cudaStreamPerThread to name a default stream). */
 int svsb200_search(
     svsb200_index* index, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
     size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists,
@@ -106,6 +107,10 @@ int svsb200_search_device(
  * Counting is off by default; enable it before the search. */
 int svsb200_set_counting(svsb200_index* index, int enabled);
 int svsb200_get_counters(svsb200_index* index, size_t nq, uint32_t* hops, uint32_t* evals);
+/* Rows of base vectors the kernel actually read per query (entry point included): equal to
+ * `evals` with the visited filter off, smaller with it on.  This -- not the reference-
+ * equivalent `evals` -- is what the HBM roofline of the kernel is computed from. */
+int svsb200_get_fetched(svsb200_index* index, size_t nq, uint32_t* fetched);
 /* Duration in milliseconds of the search kernel of the last svsb200_search* call on this
  * index (CUDA events on the launching stream; synchronises on the stop event). */
 int svsb200_last_kernel_ms(svsb200_index* index, float* ms);
@@ -113,7 +118,9 @@ int svsb200_last_kernel_ms(svsb200_index* index, float* ms);
 uint64_t svsb200_launch_count(void);
 
 /* Tuning knobs (performance only; results never change):
- *   "warps_per_cta", "ctas_per_sm", "rows_in_flight". 0 restores the default. */
+ *   "warps_per_cta", "ctas_per_sm", "rows_in_flight" (0 restores the default);
+ *   "visited_filter_slots": size of the per-query exact visited filter, the GPU form of
+ *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n). */
 int svsb200_set_option(svsb200_index* index, const char* name, long value);
 
 /* Mode B of SURVEY.md §8e -- merge per-shard top-k lists (after an NCCL all-gather) into a

@@ -21,6 +21,18 @@ DTYPE_CODES = {np.dtype(np.float32): 0, np.dtype(np.float16): 1, np.dtype(np.int
 METRIC_CODES = {"l2": 0, "ip": 1, "cosine": 2}
 
 
+def effective_cpus() -> int:
+    """min(affinity, cgroup quota): the reference's spin-waiting pool must not be oversubscribed."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
+
+
 def _code(arr: np.ndarray) -> int:
     return DTYPE_CODES[arr.dtype]
 
@@ -176,7 +188,7 @@ class RefLib(_Base):
         """Reference ``auto_build``; returns (graph uint32[n][R+1] degree-first, entry_point)."""
         d = _c(data)
         n = d.shape[0]
-        threads = threads or (os.cpu_count() or 1)
+        threads = threads or effective_cpus()
         if alpha is None:
             alpha = 1.2 if metric == "l2" else 0.95
         # Defaults of index/vamana/index.h:1081-1095.

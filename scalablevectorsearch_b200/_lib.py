@@ -17,7 +17,7 @@ SYMBOLS = [
     "svsb200_index_create", "svsb200_index_destroy", "svsb200_index_size",
     "svsb200_index_dimensions", "svsb200_index_max_degree", "svsb200_index_device_bytes",
     "svsb200_index_device", "svsb200_search", "svsb200_search_device", "svsb200_set_counting",
-    "svsb200_get_counters", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option",
+    "svsb200_get_counters", "svsb200_get_fetched", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option",
     "svsb200_merge_topk_device", "svsb200_exhaustive_device",
 ]
 
@@ -51,6 +51,7 @@ def lib() -> C.CDLL:
     l.svsb200_search_device.argtypes = [vp, vp, i32, sz, sz, sz, sz, i32, vp, i32, vp, vp]
     l.svsb200_set_counting.argtypes = [vp, i32]
     l.svsb200_get_counters.argtypes = [vp, sz, vp, vp]
+    l.svsb200_get_fetched.argtypes = [vp, sz, vp]
     l.svsb200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     l.svsb200_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     l.svsb200_merge_topk_device.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, i32, vp]

@@ -47,6 +47,9 @@ struct SearchParams {
     uint32_t k, window, capacity;
     uint32_t cap_pad;          // capacity+1 rounded up to 32
     uint32_t deg_pad;          // gstride rounded up to 32
+    uint32_t filter_slots;     // per-query exact visited filter (power of two, 0 = off)
+    uint32_t prefetch_rows;    // 1: L2-prefetch all candidate rows of a hop before the register passes
+    uint32_t prefetch_adj;     // L2-prefetch the adjacency rows of the next P unvisited buffer entries
     // outputs
     void* out_ids;
     int id_bytes;
@@ -55,6 +58,7 @@ struct SearchParams {
     unsigned int* work_counter;  // dynamic query scheduler
     uint32_t* hops;              // optional per-query counters
     uint32_t* evals;
+    uint32_t* fetched;           // rows actually read from HBM (after the visited filter)
 };
 
 struct LaunchConfig {
@@ -65,10 +69,12 @@ struct LaunchConfig {
 };
 
 // Per-warp shared-memory footprint of the search kernel (bytes), mirrored on the host.
-__host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad) {
+__host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad,
+                                                  uint32_t filter_slots) {
     // query (fp32 or bytes, reserve fp32) + buffer keys/ids + candidate keys/ids +
-    // survivor keys/pos/ids/final-pos
-    return size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 + size_t(deg_pad) * 16;
+    // survivor keys/pos/ids/final-pos + visited filter
+    return size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 + size_t(deg_pad) * 16 +
+           size_t(filter_slots) * 4;
 }
 
 // One launcher per (row type, op); defined in search_<type>.cu.

@@ -87,6 +87,12 @@ template <> struct Row<SVSB200_U8> {
     }
 };
 
+// Fire-and-forget L2 prefetch: costs no registers, so the bytes in flight per warp are not
+// bounded by the register file; the later 128-bit loads then hit L2 instead of HBM.
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 // One accumulate step of the op (euclidean.h:247-250, inner_product.h:206-208,
 // cosine.h:238-241).  Explicit _rn intrinsics: never contracted, never reordered.
 template <int OP> __device__ __forceinline__ void accumulate(float& s, float& nrm, float x, float y) {
@@ -320,7 +326,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
     const int g = lane / G;      // group inside the warp
     const int t = lane % G;      // thread inside the group
 
-    unsigned char* wbase = smem_raw + size_t(warp) * warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad);
+    unsigned char* wbase = smem_raw + size_t(warp) * warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots);
     float* q_s = reinterpret_cast<float*>(wbase);
     float* bkey = q_s + p.qstride;                                      // [cap_pad] sort keys
     uint32_t* bid = reinterpret_cast<uint32_t*>(bkey + p.cap_pad);      // [cap_pad] id | visited
@@ -330,6 +336,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
     uint32_t* spos = reinterpret_cast<uint32_t*>(skey + p.deg_pad);
     uint32_t* sid = spos + p.deg_pad;
     uint32_t* sfp = sid + p.deg_pad;
+    uint32_t* filt = sfp + p.deg_pad;                                   // [filter_slots] visited ids
 
     const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
     const uint32_t C = p.capacity, W = p.window;
@@ -352,6 +359,10 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
             for (uint32_t i = lane; i < p.qstride; i += 32) q_s[i] = src[i];
         }
         const float aux0 = p.qaux[2 * size_t(q)], aux1 = p.qaux[2 * size_t(q) + 1];
+        // Visited filter (the reference's optional VisitedFilter, index/vamana/filter.h:49-130,
+        // here direct-mapped with full ids: false negatives possible, never a false positive,
+        // so skipping a hit cannot change the result -- search_buffer.h:420).
+        for (uint32_t i = lane; i < p.filter_slots; i += 32) filt[i] = kNoNeighbor;
         __syncwarp();
 
         // Distance of up to NROWS rows per group; thread t==0 of each group publishes keys.
@@ -375,7 +386,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
         };
 
         // ---- EntryPointInitializer (greedy_search.h:62-94): clear, push entry point ----
-        uint32_t size = 1, cursor = 0, n_hops = 0, n_evals = 1;
+        uint32_t size = 1, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
         {
             uint32_t ids[NROWS];
             bool on[NROWS];
@@ -412,24 +423,59 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
             }
             if (!found) break;   // done()
             const uint32_t node = bid[pos];
+            if (p.prefetch_adj) {
+                // The entries right behind the chosen one are the likeliest next expansions:
+                // pull their adjacency rows towards L2 now (a wasted prefetch costs one row).
+                const uint32_t j = pos + 1 + lane;
+                if (lane < p.prefetch_adj && j < upper) {
+                    const uint32_t e = bid[j];
+                    if (!(e & kVisitedBit)) {
+                        const char* a = reinterpret_cast<const char*>(p.graph + size_t(e) * p.gstride);
+                        for (uint32_t off = 0; off < p.gstride * 4; off += 128) prefetch_l2(a + off);
+                    }
+                }
+            }
             __syncwarp();
             if (lane == 0) bid[pos] = node | kVisitedBit;
             cursor = pos + 1;
 
-            // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding
+            // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding.
+            // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
             const uint32_t* grow = p.graph + size_t(node) * p.gstride;
-            uint32_t deg = 0;
+            const uint32_t fmask = p.filter_slots - 1;
+            uint32_t deg = 0, ncand = 0;
             for (uint32_t j0 = 0; j0 < p.gstride; j0 += 32) {
                 uint32_t j = j0 + lane;
                 uint32_t nb = (j < p.gstride) ? __ldg(grow + j) : kNoNeighbor;
-                cid[j] = nb;
-                deg += __popc(__ballot_sync(FULL, nb != kNoNeighbor));
+                bool fresh = nb != kNoNeighbor;
+                deg += __popc(__ballot_sync(FULL, fresh));
+                if (p.filter_slots && fresh) {
+                    // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember
+                    const uint32_t slot = nb & fmask;
+                    fresh = filt[slot] != nb;
+                    if (fresh) filt[slot] = nb;
+                }
+                const unsigned m = __ballot_sync(FULL, fresh);
+                if (fresh) cid[ncand + __popc(m & ((1u << lane) - 1u))] = nb;
+                ncand += __popc(m);
+                __syncwarp();
             }
-            __syncwarp();
             ++n_hops;
             // tracker.visited(node, neighbors.size()) (greedy_search.h:165) counts the row as
             // the reference stores it, i.e. including the repeated ids removed at upload.
             n_evals += p.hops ? uint32_t(__ldg(p.ref_degree + node)) : deg;
+            n_fetched += ncand;
+            if (ncand == 0) continue;
+            deg = ncand;   // from here on: the candidates that are actually evaluated
+            if (p.prefetch_rows && deg > NROWS * GROUPS) {
+                // More candidates than one register pass covers: start every row's HBM fetch now.
+                __syncwarp();
+                const uint32_t lines = (p.row_stride + 127) >> 7;
+                for (uint32_t i = NROWS * GROUPS * lines + lane; i < deg * lines; i += 32) {
+                    const uint32_t r = i / lines, ln = i - r * lines;
+                    prefetch_l2(vectors + size_t(cid[r]) * p.row_stride + ln * 128);
+                }
+            }
 
             // neighbour expansion: distance of every neighbour (greedy_search.h:190-201)
             for (uint32_t base = 0; base < deg; base += NROWS * GROUPS) {
@@ -553,6 +599,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
         if (p.hops && lane == 0) {
             p.hops[q] = n_hops;
             p.evals[q] = n_evals;
+            p.fetched[q] = n_fetched;
         }
         __syncwarp();
     }

@@ -69,7 +69,7 @@ struct svsb200_index {
     // scratch, grown on demand
     DeviceBuffer<unsigned char> q_raw, q_codes, ids;
     DeviceBuffer<float> q_f32, q_aux, dists;
-    DeviceBuffer<uint32_t> hops, evals;
+    DeviceBuffer<uint32_t> hops, evals, fetched;
     unsigned int* d_counter = nullptr;
     int counting = 0;
     size_t counted_nq = 0;
@@ -77,7 +77,7 @@ struct svsb200_index {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     // options
-    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0;
+    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, prefetch_rows = -1, prefetch_adj = -1;
     std::mutex mutex;
 };
 
@@ -438,6 +438,7 @@ int svsb200_index_destroy(svsb200_index* ix) {
     ix->dists.release();
     ix->hops.release();
     ix->evals.release();
+    ix->fetched.release();
     if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
     if (ix->ev_start) cudaEventDestroy(ix->ev_start);
     if (ix->ev_stop) cudaEventDestroy(ix->ev_stop);
@@ -469,6 +470,16 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
     } else if (key == "rows_in_flight") {
         if (value < 0 || value > 2) return fail("rows_in_flight must be in [0, 2]");
         ix->rows_in_flight = value;
+    } else if (key == "prefetch_rows") {
+        ix->prefetch_rows = value;
+    } else if (key == "prefetch_adj") {
+        if (value > 32) return fail("prefetch_adj must be <= 32");
+        ix->prefetch_adj = value;
+    } else if (key == "visited_filter_slots") {
+        // -1 = default; 0 = off; otherwise a power of two
+        if (value > 0 && (value & (value - 1))) return fail("visited_filter_slots must be a power of two");
+        if (value > 16384) return fail("visited_filter_slots must be <= 16384");
+        ix->filter_slots = value;
     } else {
         return fail("svsb200_set_option: unknown option " + key);
     }
@@ -515,6 +526,7 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     if (ix->counting) {
         CUDA_TRY(ix->hops.ensure(nq));
         CUDA_TRY(ix->evals.ensure(nq));
+        CUDA_TRY(ix->fetched.ensure(nq));
         ix->counted_nq = nq;
     }
 
@@ -569,9 +581,13 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.work_counter = ix->d_counter;
     p.hops = ix->counting ? ix->hops.ptr : nullptr;
     p.evals = ix->counting ? ix->evals.ptr : nullptr;
+    p.fetched = ix->counting ? ix->fetched.ptr : nullptr;
+    p.filter_slots = ix->filter_slots < 0 ? 2048u : uint32_t(ix->filter_slots);
+    p.prefetch_rows = ix->prefetch_rows < 0 ? 1u : uint32_t(ix->prefetch_rows);
+    p.prefetch_adj = ix->prefetch_adj < 0 ? 4u : uint32_t(ix->prefetch_adj);
 
     LaunchConfig cfg{};
-    const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad);
+    const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots);
     int warps = ix->warps_per_cta ? int(ix->warps_per_cta) : 4;
     const size_t smem_limit = 227 * 1024;
     while (warps > 1 && per_warp * warps > smem_limit) warps >>= 1;
@@ -632,6 +648,15 @@ int svsb200_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq
     CUDA_TRY(cudaMemcpyAsync(out_ids, ix->ids.ptr, nq * k * size_t(id_bytes), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaMemcpyAsync(out_dists, ix->dists.ptr, nq * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
+    return 0;
+}
+
+int svsb200_get_fetched(svsb200_index* ix, size_t nq, uint32_t* fetched) {
+    if (!ix || !fetched) return fail("svsb200_get_fetched: NULL argument");
+    if (!ix->counting || ix->counted_nq < nq) return fail("svsb200_get_fetched: counting was not enabled for that many queries");
+    CUDA_TRY(cudaSetDevice(ix->device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(fetched, ix->fetched.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 

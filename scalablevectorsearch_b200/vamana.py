@@ -248,6 +248,11 @@ class Vamana:
         _lib.check(self._lib.svsb200_get_counters(self._h, nq, hops.ctypes.data, evals.ctypes.data))
         return hops, evals
 
+    def fetched(self, nq: int):
+        out = np.empty(nq, dtype=np.uint32)
+        _lib.check(self._lib.svsb200_get_fetched(self._h, nq, out.ctypes.data))
+        return out
+
     def last_kernel_ms(self) -> float:
         ms = C.c_float()
         _lib.check(self._lib.svsb200_last_kernel_ms(self._h, C.byref(ms)))

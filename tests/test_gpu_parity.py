@@ -73,6 +73,25 @@ def test_counters_match_reference_tracker(dataset, ref_outputs, metric):
     hops, evals = index.counters(64)
     assert np.array_equal(hops, ref_outputs[f"{metric}_counts_w32_c48_hops"])
     assert np.array_equal(evals, ref_outputs[f"{metric}_counts_w32_c48_evals"])
+    fetched = index.fetched(64)
+    assert np.all(fetched <= evals) and np.all(fetched >= hops)
+
+
+@pytest.mark.parametrize("slots", [0, 64, 1024, 16384])
+def test_visited_filter_never_changes_results(dataset, ref_outputs, slots):
+    """search_buffer.h:420 "Visited set use does not affect accuracy": any filter size, same bits."""
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    index.set_option("visited_filter_slots", slots)
+    index.set_counting(True)
+    got = search(index, dataset.queries[100:], 10, 22, 23)
+    assert_same(got, ref_outputs["l2_f32_f32_w22_c23_ids"], ref_outputs["l2_f32_f32_w22_c23_dists"], f"filter {slots}")
+    hops, evals = index.counters(900)
+    fetched = index.fetched(900)
+    if slots == 0:
+        # without the filter every neighbour is read, except the in-row repeats removed at upload
+        assert np.all(fetched <= evals) and fetched.sum() > 0.98 * evals.sum()
+    else:
+        assert fetched.sum() < evals.sum()
 
 
 @pytest.mark.parametrize("dim,max_degree", [(17, 8), (96, 64), (100, 32), (223, 24), (768, 16)])
