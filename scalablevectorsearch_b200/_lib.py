@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvsb200.so")
+# SVSB200_LIB lets experiments point at an alternative build; the default is the in-tree library.
+LIB_PATH = os.environ.get("SVSB200_LIB") or os.path.join(_HERE, "libsvsb200.so")
 
 #: every symbol ``include/svsb200.h`` declares (checked by tests/test_abi.py)
 SYMBOLS = [

@@ -48,7 +48,8 @@ struct SearchParams {
     uint32_t cap_pad;          // capacity+1 rounded up to 32
     uint32_t deg_pad;          // gstride rounded up to 32
     uint32_t filter_slots;     // per-query exact visited filter (power of two, 0 = off)
-    uint32_t prefetch_rows;    // 1: L2-prefetch all candidate rows of a hop before the register passes
+    uint32_t filter_shift;     // log2(filter_slots)
+    uint32_t filter_tag16;     // 1: entries are 16-bit tags id >> filter_shift (exact while n <= slots * 65535)
     uint32_t prefetch_adj;     // L2-prefetch the adjacency rows of the next P unvisited buffer entries
     // outputs
     void* out_ids;
@@ -70,11 +71,11 @@ struct LaunchConfig {
 
 // Per-warp shared-memory footprint of the search kernel (bytes), mirrored on the host.
 __host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad,
-                                                  uint32_t filter_slots) {
+                                                  uint32_t filter_bytes) {
     // query (fp32 or bytes, reserve fp32) + buffer keys/ids + candidate keys/ids +
     // survivor keys/pos/ids/final-pos + visited filter
     return size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 + size_t(deg_pad) * 16 +
-           size_t(filter_slots) * 4;
+           size_t(filter_bytes);
 }
 
 // One launcher per (row type, op); defined in search_<type>.cu.

@@ -314,7 +314,10 @@ __device__ __forceinline__ float finish_distance(const SearchParams& p, float su
 // The kernel.
 // ---------------------------------------------------------------------------------------
 template <int ROWT, int OP, int DS, int NROWS>
-__global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constant__ SearchParams p) {
+#ifndef SVSB200_MIN_BLOCKS
+#define SVSB200_MIN_BLOCKS 2   // <= 128 registers: four 4-warp CTAs (16 warps) per SM
+#endif
+__global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(const __grid_constant__ SearchParams p) {
     constexpr bool kInt = (OP >= OP_L2I);
     constexpr int G = kInt ? 4 : 16 / Row<ROWT>::LPT;     // threads per row
     constexpr int GROUPS = 32 / G;                        // rows per warp per slot
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
     const int g = lane / G;      // group inside the warp
     const int t = lane % G;      // thread inside the group
 
-    unsigned char* wbase = smem_raw + size_t(warp) * warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots);
+    unsigned char* wbase = smem_raw + size_t(warp) * warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
     float* q_s = reinterpret_cast<float*>(wbase);
     float* bkey = q_s + p.qstride;                                      // [cap_pad] sort keys
     uint32_t* bid = reinterpret_cast<uint32_t*>(bkey + p.cap_pad);      // [cap_pad] id | visited
@@ -336,7 +339,8 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
     uint32_t* spos = reinterpret_cast<uint32_t*>(skey + p.deg_pad);
     uint32_t* sid = spos + p.deg_pad;
     uint32_t* sfp = sid + p.deg_pad;
-    uint32_t* filt = sfp + p.deg_pad;                                   // [filter_slots] visited ids
+    uint32_t* filt = sfp + p.deg_pad;                                   // [filter_slots] visited ids (or 16-bit tags)
+    uint16_t* filt16 = reinterpret_cast<uint16_t*>(filt);
 
     const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
     const uint32_t C = p.capacity, W = p.window;
@@ -362,7 +366,7 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
         // Visited filter (the reference's optional VisitedFilter, index/vamana/filter.h:49-130,
         // here direct-mapped with full ids: false negatives possible, never a false positive,
         // so skipping a hit cannot change the result -- search_buffer.h:420).
-        for (uint32_t i = lane; i < p.filter_slots; i += 32) filt[i] = kNoNeighbor;
+        for (uint32_t i = lane; i < (p.filter_tag16 ? p.filter_slots / 2 : p.filter_slots); i += 32) filt[i] = kNoNeighbor;
         __syncwarp();
 
         // Distance of up to NROWS rows per group; thread t==0 of each group publishes keys.
@@ -452,8 +456,15 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
                 if (p.filter_slots && fresh) {
                     // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember
                     const uint32_t slot = nb & fmask;
-                    fresh = filt[slot] != nb;
-                    if (fresh) filt[slot] = nb;
+                    if (p.filter_tag16) {
+                        // slot index + 16-bit tag reconstruct the full id: still exact
+                        const uint16_t tag = uint16_t(nb >> p.filter_shift);
+                        fresh = filt16[slot] != tag;
+                        if (fresh) filt16[slot] = tag;
+                    } else {
+                        fresh = filt[slot] != nb;
+                        if (fresh) filt[slot] = nb;
+                    }
                 }
                 const unsigned m = __ballot_sync(FULL, fresh);
                 if (fresh) cid[ncand + __popc(m & ((1u << lane) - 1u))] = nb;
@@ -467,15 +478,6 @@ __global__ void __launch_bounds__(256) vamana_search_kernel(const __grid_constan
             n_fetched += ncand;
             if (ncand == 0) continue;
             deg = ncand;   // from here on: the candidates that are actually evaluated
-            if (p.prefetch_rows && deg > NROWS * GROUPS) {
-                // More candidates than one register pass covers: start every row's HBM fetch now.
-                __syncwarp();
-                const uint32_t lines = (p.row_stride + 127) >> 7;
-                for (uint32_t i = NROWS * GROUPS * lines + lane; i < deg * lines; i += 32) {
-                    const uint32_t r = i / lines, ln = i - r * lines;
-                    prefetch_l2(vectors + size_t(cid[r]) * p.row_stride + ln * 128);
-                }
-            }
 
             // neighbour expansion: distance of every neighbour (greedy_search.h:190-201)
             for (uint32_t base = 0; base < deg; base += NROWS * GROUPS) {

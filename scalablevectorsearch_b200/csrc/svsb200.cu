@@ -77,7 +77,7 @@ struct svsb200_index {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     // options
-    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, prefetch_rows = -1, prefetch_adj = -1;
+    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, prefetch_adj = -1, filter_tag16 = 1;
     std::mutex mutex;
 };
 
@@ -470,8 +470,8 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
     } else if (key == "rows_in_flight") {
         if (value < 0 || value > 2) return fail("rows_in_flight must be in [0, 2]");
         ix->rows_in_flight = value;
-    } else if (key == "prefetch_rows") {
-        ix->prefetch_rows = value;
+    } else if (key == "filter_tag16") {
+        ix->filter_tag16 = value;
     } else if (key == "prefetch_adj") {
         if (value > 32) return fail("prefetch_adj must be <= 32");
         ix->prefetch_adj = value;
@@ -582,12 +582,15 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.hops = ix->counting ? ix->hops.ptr : nullptr;
     p.evals = ix->counting ? ix->evals.ptr : nullptr;
     p.fetched = ix->counting ? ix->fetched.ptr : nullptr;
-    p.filter_slots = ix->filter_slots < 0 ? 2048u : uint32_t(ix->filter_slots);
-    p.prefetch_rows = ix->prefetch_rows < 0 ? 1u : uint32_t(ix->prefetch_rows);
+    p.filter_slots = ix->filter_slots < 0 ? 4096u : uint32_t(ix->filter_slots);
+    p.filter_shift = 0;
+    while ((1u << p.filter_shift) < p.filter_slots) ++p.filter_shift;
+    // 16-bit tags are exact as long as every id >> shift fits below the 0xFFFF "empty" mark
+    p.filter_tag16 = p.filter_slots && ((uint64_t(ix->n - 1) >> p.filter_shift) < 0xFFFFull) && ix->filter_tag16 != 0;
     p.prefetch_adj = ix->prefetch_adj < 0 ? 4u : uint32_t(ix->prefetch_adj);
 
     LaunchConfig cfg{};
-    const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots);
+    const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
     int warps = ix->warps_per_cta ? int(ix->warps_per_cta) : 4;
     const size_t smem_limit = 227 * 1024;
     while (warps > 1 && per_warp * warps > smem_limit) warps >>= 1;
