@@ -124,11 +124,12 @@ class ShardedSearch:
         ids = torch.where(valid, ids + self.id_offset, ids)
         if world == 1:
             return ids, dists
-        all_ids = torch.empty((world,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-        all_d = torch.empty((world,) + tuple(dists.shape), dtype=dists.dtype, device=dists.device)
+        nq = ids.shape[0]
+        all_ids = torch.empty((world * nq, k), dtype=ids.dtype, device=ids.device)
+        all_d = torch.empty((world * nq, k), dtype=dists.dtype, device=dists.device)
         dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=self.group)
         dist.all_gather_into_tensor(all_d, dists.contiguous(), group=self.group)
-        return self.merge(all_ids, all_d, k, self.greater)
+        return self.merge(all_ids.view(world, nq, k), all_d.view(world, nq, k), k, self.greater)
 
 
 def _stream_handle(device) -> int:
