@@ -1,0 +1,179 @@
+// gpu_vamana_index.h -- C++ host side of the drop-in boundary.
+//
+// `svsb200::GpuVamanaIndex<Graph, Data, Dist>` is the reference's static Vamana index
+// (include/svs/index/vamana/index.h:276-942) with its *batch search* re-pointed at
+// libsvsb200.so.  It derives from the reference class, so every member the orchestrator
+// needs (`orchestrators/vamana.h:127-275`, `orchestrators/manager.h:130-186`: parameters,
+// save, reconstruct_at, calibrate, get_distance, batch iterators ...) is the reference's own
+// code, unmodified, and only
+//
+//     search(QueryResultView<I>, queries, VamanaSearchParameters, cancel)   (index.h:564-611)
+//
+// is replaced.  Because `ManagerImpl::search` calls `impl().search(...)` on the static type
+// (`manager.h:141-166` -> `index/index.h:44-55`), wrapping it with the reference's own factory
+//
+//     svs::Vamana v = svs::make_vamana<svs::lib::Types<float>>(
+//         svsb200::GpuVamanaIndex{std::move(cpu_index), /*device=*/0});
+//
+// yields a stock type-erased `svs::Vamana` whose `search` runs on the GPU -- the object that
+// `utils/search_index.cpp`, `bindings/python` and `bindings/cpp` hold.
+//
+// This header compiles against the reference headers (`-I<reference>/include`); it contains
+// no reference code.  Errors from the C ABI are rethrown as svs::ANNException
+// (include/svs/lib/exception.h), the reference's own convention.
+#pragma once
+
+#include "svs/index/vamana/index.h"
+#include "svs/quantization/scalar/scalar.h"
+
+#include "svsb200.h"
+
+#include <memory>
+#include <type_traits>
+
+namespace svsb200 {
+
+namespace detail {
+template <typename T> struct DTypeCode;
+template <> struct DTypeCode<float> { static constexpr int value = SVSB200_F32; };
+template <> struct DTypeCode<svs::Float16> { static constexpr int value = SVSB200_F16; };
+template <> struct DTypeCode<int8_t> { static constexpr int value = SVSB200_I8; };
+template <> struct DTypeCode<uint8_t> { static constexpr int value = SVSB200_U8; };
+
+template <typename Dist> struct MetricCode;
+template <> struct MetricCode<svs::distance::DistanceL2> { static constexpr int value = SVSB200_L2; };
+template <> struct MetricCode<svs::distance::DistanceIP> { static constexpr int value = SVSB200_IP; };
+template <> struct MetricCode<svs::distance::DistanceCosineSimilarity> {
+    static constexpr int value = SVSB200_COSINE;
+};
+
+struct HandleDeleter {
+    void operator()(svsb200_index* p) const { svsb200_index_destroy(p); }
+};
+
+inline void check(int rc) {
+    if (rc != 0) {
+        throw ANNEXCEPTION("svsb200: {}", svsb200_last_error());
+    }
+}
+} // namespace detail
+
+template <typename Graph, typename Data, typename Dist>
+class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist> {
+  public:
+    using base_type = svs::index::vamana::VamanaIndex<Graph, Data, Dist>;
+    using search_parameters_type = typename base_type::search_parameters_type;
+
+    /// Take over an assembled (or freshly built) CPU index and mirror its graph and vectors
+    /// into the HBM of `device`.  The host copies stay alive for the non-search members.
+    explicit GpuVamanaIndex(base_type&& cpu, int device = 0)
+        : base_type(std::move(cpu)) {
+        this->experimental_escape_hatch([&](const auto& graph,
+                                            const auto& data,
+                                            const auto& /*distance*/,
+                                            auto entry_points) {
+            if (entry_points.size() != 1) {
+                throw ANNEXCEPTION("GpuVamanaIndex needs exactly one entry point");
+            }
+            const auto& rows = graph.get_data(); // uint32[n][max_degree + 1], degree first
+            svsb200_index* raw = nullptr;
+            if constexpr (svs::quantization::scalar::IsSQData<Data>) {
+                using E = typename Data::element_type;
+                const float aux[2] = {data.get_scale(), data.get_bias()};
+                detail::check(svsb200_index_create(
+                    data.get_datum(0).data(),
+                    detail::DTypeCode<E>::value,
+                    data.size(),
+                    data.dimensions(),
+                    0,
+                    rows.data(),
+                    rows.dimensions(),
+                    entry_points[0],
+                    detail::MetricCode<Dist>::value,
+                    SVSB200_SQ,
+                    aux,
+                    device,
+                    &raw
+                ));
+            } else {
+                using E = std::remove_const_t<typename Data::element_type>;
+                detail::check(svsb200_index_create(
+                    data.data(),
+                    detail::DTypeCode<E>::value,
+                    data.size(),
+                    data.dimensions(),
+                    0,
+                    rows.data(),
+                    rows.dimensions(),
+                    entry_points[0],
+                    detail::MetricCode<Dist>::value,
+                    SVSB200_PLAIN,
+                    nullptr,
+                    device,
+                    &raw
+                ));
+            }
+            handle_.reset(raw, detail::HandleDeleter{});
+        });
+    }
+
+    // Single-query search, scratch-space search etc. stay the reference's.
+    using base_type::search;
+
+    /// Batch search on the GPU: same signature and semantics as index.h:564-611.
+    template <typename I, svs::data::ImmutableMemoryDataset Queries>
+    void search(
+        svs::QueryResultView<I> result,
+        const Queries& queries,
+        const search_parameters_type& sp,
+        const svs::lib::DefaultPredicate& cancel = svs::lib::Returns(svs::lib::Const<false>())
+    ) {
+        using Q = std::remove_const_t<typename Queries::element_type>;
+        static_assert(sizeof(I) == 4 || sizeof(I) == 8, "result ids must be 32 or 64 bit");
+        if (queries.dimensions() != this->dimensions()) {
+            throw ANNEXCEPTION(
+                "Query dimensions {} do not match index dimensions {}",
+                queries.dimensions(),
+                this->dimensions()
+            );
+        }
+        // The predicate cannot be polled from the device: honour it at batch granularity
+        // (the reference polls per query and per hop, greedy_search.h:155, extensions.h:579).
+        if (cancel()) {
+            return;
+        }
+        const size_t nq = queries.size();
+        if (nq == 0) {
+            return;
+        }
+        detail::check(svsb200_search(
+            handle_.get(),
+            queries.get_datum(0).data(),
+            detail::DTypeCode<Q>::value,
+            nq,
+            result.n_neighbors(),
+            sp.buffer_config_.get_search_window_size(),
+            sp.buffer_config_.get_total_capacity(),
+            sp.search_buffer_visited_set_ ? 1 : 0,
+            &result.index(0, 0),
+            static_cast<int>(sizeof(I)),
+            &result.distance(0, 0),
+            nullptr
+        ));
+    }
+
+    std::string name() const { return "GpuVamanaIndex (libsvsb200, sm_100a)"; }
+    svsb200_index* native_handle() const { return handle_.get(); }
+
+  private:
+    std::shared_ptr<svsb200_index> handle_{};
+};
+
+template <typename Graph, typename Data, typename Dist>
+GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&, int)
+    -> GpuVamanaIndex<Graph, Data, Dist>;
+template <typename Graph, typename Data, typename Dist>
+GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&)
+    -> GpuVamanaIndex<Graph, Data, Dist>;
+
+} // namespace svsb200

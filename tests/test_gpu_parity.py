@@ -149,3 +149,35 @@ def test_error_behaviour(dataset):
         index.search(dataset.queries.astype(np.int8), 10)
     ids, dists = index.search(dataset.queries[:0], 10)   # empty batch
     assert ids.shape == (0, 10)
+
+
+def test_cpp_adapter_cli_matches_python_path(dataset, ref_outputs, tmp_path):
+    """BASELINE config #1 through the C++ boundary: the reference's `search_index` CLI with a
+    GpuVamanaIndex behind `svs::Vamana` (scalablevectorsearch_b200/cpp) writes the same ids as the
+    reference's CPU path (committed outputs) for the prebuilt test graph."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    from scalablevectorsearch_b200 import io
+    exe = os.path.join(ROOT, "scalablevectorsearch_b200", "cpp", "_build", "search_index_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("search_index_gpu not built (needs the reference headers at build time)")
+    io.write_svs(str(tmp_path / "data.svs"), dataset.data)
+    io.write_svs(str(tmp_path / "graph.svs"), dataset.graph)
+    io.write_vecs(str(tmp_path / "queries.fvecs"), dataset.queries[100:])
+    (tmp_path / "config.toml").write_text(
+        "__version__ = 'v0.0.2'\n[object]\n__schema__ = 'vamana_index_parameters'\n__version__ = 'v0.0.3'\n"
+        f"entry_point = {dataset.entry_point}\nname = 'vamana index parameters'\n"
+        "[object.build_parameters]\n__schema__ = 'vamana_build_parameters'\n__version__ = 'v0.0.1'\nalpha = 1.2\n"
+        "graph_max_degree = 128\nmax_candidate_pool_size = 1000\nname = 'vamana build parameters'\nprune_to = 128\n"
+        "use_full_search_history = true\nwindow_size = 200\n"
+        "[object.search_parameters]\n__schema__ = 'vamana_search_parameters'\n__version__ = 'v0.0.1'\n"
+        "prefetch_lookahead = 0\nprefetch_step = 0\nsearch_buffer_capacity = 0\nsearch_buffer_visited_set = false\n"
+        "search_window_size = 0\n")
+    out = subprocess.run([exe, "float", "float", str(tmp_path / "queries.fvecs"), "15", "10", "2",
+                          str(tmp_path / "config.toml"), str(tmp_path / "graph.svs"), str(tmp_path / "data.svs"),
+                          str(tmp_path / "res"), "L2"], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert "GpuVamanaIndex" in out.stdout
+    ids = io.read_vecs(str(tmp_path / "res_idx.ivecs"))
+    assert np.array_equal(ids.astype(np.uint32), ref_outputs["l2_f32_f32_w15_c15_ids"])
