@@ -131,6 +131,19 @@ int svsb200_merge_topk_device(
     const uint64_t* d_ids, const float* d_dists, size_t nshards, size_t nq, size_t k, int metric,
     uint64_t* d_out_ids, float* d_out_dists, int device, void* stream);
 
+/* LVQ-8 (one-level, 8-bit locally-adaptive vector quantisation).  The reference's LVQ lives in a
+ * closed-source library (examples/cpp/shared/example_vamana_with_compression_lvq.cpp:38,
+ * `LVQDataset<8>::compress(data, threadpool, padding)`); this is an own specification
+ *  and parity with Intel's binary is unpinned.
+ *   row layout  : dim uint8 codes, padded to 4 bytes, then {delta, lower} as two IEEE float16,
+ *                 row stride = svsb200_lvq8_row_stride(dim) (a multiple of 32 bytes);
+ *   compress    : encodes n float32 vectors against `mean[dim]` on the GPU into `out_rows`
+ *                 (host buffers); pass the same `mean` as `aux` to svsb200_index_create with
+ *                 storage = SVSB200_LVQ8, dtype = SVSB200_U8, row_stride_bytes = the stride. */
+size_t svsb200_lvq8_row_stride(size_t dim);
+int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows,
+                          int device);
+
 /* Exhaustive search used by the harness for ground truth (replaces svs::Flat /
  * index/flat/flat.h:159 for recall measurement only): top-k of every query against all
  * `n` base vectors already on the device inside `index`. Distances use the same exact

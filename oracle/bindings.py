@@ -210,3 +210,27 @@ class OracleLib(_Base):
     """The plain-C restatement (``oracle/liboracle.so``)."""
     prefix = "oracle"
     path = os.path.join(HERE, "liboracle.so")
+
+    # ---- LVQ-8 (own specification; parity with Intel's closed LVQ is unpinned) ----
+    def lvq8_compress(self, data: np.ndarray, mean: np.ndarray) -> np.ndarray:
+        d, m = _c(data.astype(np.float32, copy=False)), _c(mean.astype(np.float32, copy=False))
+        self.lib.oracle_lvq8_row_stride.restype = C.c_size_t
+        self.lib.oracle_lvq8_row_stride.argtypes = [C.c_size_t]
+        stride = self.lib.oracle_lvq8_row_stride(d.shape[1])
+        rows = np.zeros((d.shape[0], stride), dtype=np.uint8)
+        self.lib.oracle_lvq8_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        self.lib.oracle_lvq8_compress(_ptr(d), d.shape[0], d.shape[1], _ptr(m), _ptr(rows))
+        return rows
+
+    def lvq8_index(self, rows: np.ndarray, dim: int, mean: np.ndarray, graph: np.ndarray, entry_point: int,
+                   metric: str) -> _Index:
+        r, m, g = _c(rows), _c(mean.astype(np.float32, copy=False)), _c(graph.astype(np.uint32, copy=False))
+        fn = self.lib.oracle_lvq8_index_create
+        fn.restype = C.c_void_p
+        fn.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_int]
+        h = fn(_ptr(r), r.shape[0], dim, _ptr(m), _ptr(g), g.shape[1] - 1, int(entry_point), METRIC_CODES[metric])
+        if not h:
+            raise RuntimeError(self._err())
+        idx = _Index(self.lib, self.prefix, h)
+        idx._keep = (r, m, g)
+        return idx

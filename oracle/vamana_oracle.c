@@ -3,7 +3,7 @@
  * TEST INFRASTRUCTURE ONLY (see vamana_oracle.h).  Every function cites the reference
  * file:line (relative to /root/reference/include/svs) whose behaviour it restates.  The
  * restatement is pinned bit-for-bit against the compiled reference (oracle/_ref) by
- * tests/test_oracle_pinned.py and against the reference's 17 golden recalls by
+ * tests/test_oracle_golden.py (live _ref comparison) and against the reference's 17 golden recalls by
  * tests/test_oracle_golden.py.
  *
  * Floating-point contract: the reference's AVX-512 kernels are a
@@ -204,6 +204,9 @@ typedef struct {
     float a_norm;      /* cosine */
     float offset;      /* SQ/IP: bias * sum(q) */
     float* row_f32;    /* scratch for the converted / decompressed row */
+    int lvq;           /* rows are LVQ-8 (own spec, see oracle_lvq8_compress) */
+    const float* mean; /* LVQ-8 dataset mean */
+    size_t lvq_const_offset;
 } FixedQuery;
 
 static int fixed_query_init(FixedQuery* f, int metric, int qtype, int dtype, int sq, size_t dim,
@@ -230,6 +233,19 @@ static void fixed_query_free(FixedQuery* f) {
 static void fix_argument(FixedQuery* f, const void* query) {
     size_t n = f->dim;
     f->q_raw = query;
+    if (f->lvq) {
+        /* LVQ-8 (own specification): L2 removes the dataset mean from the query once;
+         * IP keeps the query and adds <q, mean> (sequential fma) to every result. */
+        load_as_float(f->qtype, query, n, f->q_f32);
+        if (f->metric == ORACLE_L2) {
+            for (size_t i = 0; i < n; ++i) f->q_f32[i] = f->q_f32[i] - f->mean[i];
+        } else {
+            float acc = 0.0f;
+            for (size_t i = 0; i < n; ++i) acc = fmaf(f->q_f32[i], f->mean[i], acc);
+            f->offset = acc;
+        }
+        return;
+    }
     if (!f->sq) {
         load_as_float(f->qtype, query, n, f->q_f32);
         /* DistanceCosineSimilarity::fix_argument (cosine.h:117-119). */
@@ -275,6 +291,15 @@ static void fix_argument(FixedQuery* f, const void* query) {
 
 static float compute_distance(FixedQuery* f, const void* row) {
     size_t n = f->dim;
+    if (f->lvq) {
+        /* decode y_i = fma(delta, code_i, lower), then the reference's float tree */
+        _Float16 consts[2];
+        memcpy(consts, (const char*)row + f->lvq_const_offset, 4);
+        float delta = (float)consts[0], lower = (float)consts[1];
+        for (size_t i = 0; i < n; ++i) f->row_f32[i] = fmaf(delta, (float)((const uint8_t*)row)[i], lower);
+        if (f->metric == ORACLE_L2) return float_tree(0, f->q_f32, f->row_f32, n, NULL);
+        return float_tree(1, f->q_f32, f->row_f32, n, NULL) + f->offset;
+    }
     if (f->sq) {
         if (f->metric == ORACLE_L2) {
             /* EuclideanCompressed::compute (scalar.h:88-94): scale^2 * L2_int(qc, row). */
@@ -410,12 +435,15 @@ typedef struct {
     uint32_t* graph; /* owned copy, n x (max_degree + 1) */
     uint32_t entry_point;
     float scale, bias;
+    int lvq;
+    size_t row_stride, lvq_const_offset; /* row_stride 0 = dense */
+    float* mean;
 } Index;
 
 /* greedy_search (index/vamana/greedy_search.h:124-203) with EntryPointInitializer (:62-94). */
 static void greedy_search(const Index* ix, FixedQuery* f, const void* query, Buffer* buf,
                           uint64_t* hops, uint64_t* evals) {
-    size_t row_bytes = ix->dim * elem_size(ix->dtype);
+    size_t row_bytes = ix->row_stride ? ix->row_stride : ix->dim * elem_size(ix->dtype);
     fix_argument(f, query); /* :140 */
     buffer_clear(buf);      /* :79 */
     {
@@ -510,9 +538,70 @@ void* oracle_sq_index_create(int code_type, const float* data, size_t n, size_t 
     return ix;
 }
 
+/* ------------------------------------------------------------------------------------
+ * LVQ-8, own specification (the reference's LVQ is closed source: parity UNPINNED).
+ *   r_i = x_i - mean_i; lower = min r; upper = max r; delta = (upper - lower) / 255
+ *   {delta, lower} stored as IEEE float16 (RNE); codes against the stored constants:
+ *   c_i = clamp(rint((r_i - lower16) / delta16), 0, 255), 0 when delta16 == 0.
+ *   Row = dim codes, padded to 4 bytes, then delta16, lower16; stride multiple of 32.
+ * ---------------------------------------------------------------------------------- */
+size_t oracle_lvq8_row_stride(size_t dim) { return ((((dim + 3) / 4 * 4) + 4) + 31) / 32 * 32; }
+
+int oracle_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows) {
+    size_t stride = oracle_lvq8_row_stride(dim), off = (dim + 3) / 4 * 4;
+    for (size_t r = 0; r < n; ++r) {
+        const float* x = data + r * dim;
+        uint8_t* out = (uint8_t*)out_rows + r * stride;
+        memset(out, 0, stride);
+        float lo = INFINITY, hi = -INFINITY;
+        for (size_t i = 0; i < dim; ++i) {
+            float v = x[i] - mean[i];
+            lo = v < lo ? v : lo;
+            hi = v > hi ? v : hi;
+        }
+        float range = hi - lo;
+        _Float16 consts[2] = {(_Float16)(range / 255.0f), (_Float16)lo};
+        float d = (float)consts[0], l = (float)consts[1];
+        for (size_t i = 0; i < dim && d > 0.0f; ++i) {
+            float v = x[i] - mean[i];
+            float q = rintf((v - l) / d);
+            q = q < 0.0f ? 0.0f : (q > 255.0f ? 255.0f : q);
+            out[i] = (uint8_t)(int)q;
+        }
+        memcpy(out + off, consts, 4);
+    }
+    return 0;
+}
+
+void* oracle_lvq8_index_create(const void* rows, size_t n, size_t dim, const float* mean,
+                               const uint32_t* graph_rows, size_t max_degree, uint32_t entry_point, int metric) {
+    if (metric == ORACLE_COS) {
+        snprintf(g_error, sizeof(g_error), "LVQ-8: cosine is not supported");
+        return NULL;
+    }
+    Index* ix = index_new(ORACLE_U8, NULL, 0, dim, graph_rows, max_degree, entry_point, metric);
+    if (!ix) return NULL;
+    /* index_new sized the graph for 0 nodes: redo with the real count */
+    free(ix->graph);
+    free(ix->data);
+    ix->n = n;
+    ix->row_stride = oracle_lvq8_row_stride(dim);
+    ix->lvq_const_offset = (dim + 3) / 4 * 4;
+    ix->lvq = 1;
+    ix->data = malloc(n * ix->row_stride);
+    ix->graph = (uint32_t*)malloc(n * (max_degree + 1) * sizeof(uint32_t));
+    ix->mean = (float*)malloc(dim * sizeof(float));
+    if (!ix->data || !ix->graph || !ix->mean) return NULL;
+    memcpy(ix->data, rows, n * ix->row_stride);
+    memcpy(ix->graph, graph_rows, n * (max_degree + 1) * sizeof(uint32_t));
+    memcpy(ix->mean, mean, dim * sizeof(float));
+    return ix;
+}
+
 void oracle_index_destroy(void* h) {
     Index* ix = (Index*)h;
     if (!ix) return;
+    free(ix->mean);
     free(ix->data);
     free(ix->graph);
     free(ix);
@@ -521,7 +610,7 @@ void oracle_index_destroy(void* h) {
 static int run_batch(Index* ix, int qtype, const void* queries, size_t nq, size_t k, size_t window,
                      size_t capacity, int visited_set, uint64_t* ids, float* dists, uint64_t* hops,
                      uint64_t* evals) {
-    if (ix->sq ? !(qtype == ORACLE_F32 || qtype == ORACLE_F16) : !pair_supported(qtype, ix->dtype))
+    if ((ix->sq || ix->lvq) ? !(qtype == ORACLE_F32 || qtype == ORACLE_F16) : !pair_supported(qtype, ix->dtype))
         FAIL("unsupported (query,data) pair %d %d", qtype, ix->dtype);
     if (window > capacity) FAIL("search window %zu exceeds capacity %zu", window, capacity);
     /* VamanaIndex::search (index/vamana/index.h:590-592): a buffer smaller than k is
@@ -537,6 +626,9 @@ static int run_batch(Index* ix, int qtype, const void* queries, size_t nq, size_
     FixedQuery f;
     if (!buf.e || fixed_query_init(&f, ix->metric, qtype, ix->dtype, ix->sq, ix->dim, ix->scale, ix->bias))
         FAIL("out of memory");
+    f.lvq = ix->lvq;
+    f.mean = ix->mean;
+    f.lvq_const_offset = ix->lvq_const_offset;
     size_t qbytes = ix->dim * elem_size(qtype);
     for (size_t q = 0; q < nq; ++q) {
         uint64_t h = 0, e = 0;

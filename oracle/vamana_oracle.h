@@ -33,6 +33,11 @@ void* oracle_sq_index_create(int code_type, const float* data, size_t n, size_t 
                              const uint32_t* graph_rows, size_t max_degree, uint32_t entry_point,
                              int metric, size_t threads, float* scale_out, float* bias_out,
                              void* codes_out);
+/* LVQ-8 (own specification; the reference's LVQ is closed source, parity unpinned). */
+size_t oracle_lvq8_row_stride(size_t dim);
+int oracle_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows);
+void* oracle_lvq8_index_create(const void* rows, size_t n, size_t dim, const float* mean,
+                               const uint32_t* graph_rows, size_t max_degree, uint32_t entry_point, int metric);
 void oracle_index_destroy(void* index);
 int oracle_index_search(void* index, int qtype, const void* queries, size_t nq, size_t k,
                         size_t window, size_t capacity, int visited_set, uint64_t* ids,

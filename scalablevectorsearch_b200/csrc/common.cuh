@@ -17,6 +17,10 @@ constexpr uint32_t kNoNeighbor = 0xFFFFFFFFu;   // padding of adjacency rows in 
 constexpr uint32_t kVisitedBit = 0x80000000u;   // SearchNeighbor::visited packed into the id
 constexpr uint32_t kIdMask = 0x7FFFFFFFu;
 
+// Internal row kinds of the search kernel: the four ABI element types plus LVQ-8 rows
+// (uint8 codes followed by the per-vector {delta, lower} as two float16).
+constexpr int ROW_LVQ8 = 4;
+
 // Distance operator of the search kernel.
 //   *F: the reference's fp32 expression tree (generic_simd_op, simd_utils.h:204-252)
 //   *I: exact int32 arithmetic for (int8,int8)/(uint8,uint8) (L2VNNIOp/IPVNNIOp)
@@ -31,11 +35,13 @@ struct SearchParams {
     uint32_t n;
     uint32_t dim;
     uint32_t row_stride;
+    uint32_t lvq_const_offset;  // LVQ-8: byte offset of {delta, lower} (2 x f16) inside a row
     uint32_t gstride;
     uint32_t entry_point;
     // distance post-processing
     int greater;               // comparator std::greater (IP / cosine): keys are negated
     int sq;                    // rows are scalar-quantised codes
+    int lvq;                   // rows are LVQ-8 (mean-removed, per-vector delta/lower)
     float scale, bias, scale_sq;
     // prepared queries (output of prepare_queries)
     const float* qf;           // [nq][qstride] fp32 operands of the float tree

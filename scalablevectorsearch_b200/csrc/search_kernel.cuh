@@ -87,6 +87,9 @@ template <> struct Row<SVSB200_U8> {
     }
 };
 
+// LVQ-8 rows: uint8 codes; decompression y = fma(delta, code, lower) happens in float_rows.
+template <> struct Row<ROW_LVQ8> : Row<SVSB200_U8> {};
+
 // Fire-and-forget L2 prefetch: costs no registers, so the bytes in flight per warp are not
 // bounded by the register file; the later 128-bit loads then hit L2 instead of HBM.
 __device__ __forceinline__ void prefetch_l2(const void* p) {
@@ -144,6 +147,29 @@ __device__ __forceinline__ void float_rows(
     constexpr int LPT = R::LPT;
     const int D = DS ? DS : int(p.dim);
     const bool sqcos = (OP == OP_COSF) && p.sq;
+    // LVQ-8: per-vector constants, two float16 right behind the codes.
+    float lvq_delta[NROWS], lvq_lower[NROWS];
+    if constexpr (ROWT == ROW_LVQ8) {
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+            lvq_delta[r] = 0.f;
+            lvq_lower[r] = 0.f;
+            if (rowp[r]) {
+                const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rowp[r] + p.lvq_const_offset));
+                const __half2 h = *reinterpret_cast<const __half2*>(&c);
+                lvq_delta[r] = __low2float(h);
+                lvq_lower[r] = __high2float(h);
+            }
+        }
+    }
+    // element as the distance tree sees it
+    auto element = [&](int r, float y) -> float {
+        if constexpr (ROWT == ROW_LVQ8) {
+            return __fmaf_rn(lvq_delta[r], y, lvq_lower[r]);
+        } else {
+            return sqcos ? __fadd_rn(__fmul_rn(p.scale, y), p.bias) : y;
+        }
+    };
 
     float s[NROWS][4][LPT];
     float n[NROWS][4][LPT];
@@ -183,7 +209,7 @@ __device__ __forceinline__ void float_rows(
                 R::cvt(raw[r][k], y);
 #pragma unroll
                 for (int l = 0; l < LPT; ++l) {
-                    float yy = sqcos ? __fadd_rn(__fmul_rn(p.scale, y[l]), p.bias) : y[l];
+                    float yy = element(r, y[l]);
                     accumulate<OP>(s[r][k][l], n[r][k][l], x[l], yy);
                 }
             }
@@ -228,7 +254,7 @@ __device__ __forceinline__ void float_rows(
 #pragma unroll
                     for (int l = 0; l < LPT; ++l) {
                         if (e0 + l < D) {
-                            float yy = sqcos ? __fadd_rn(__fmul_rn(p.scale, y[l]), p.bias) : y[l];
+                            float yy = element(r, y[l]);
                             accumulate<OP>(s[r][0][l], n[r][0][l], x[l], yy);
                         }
                     }
@@ -292,7 +318,8 @@ __device__ __forceinline__ float finish_distance(const SearchParams& p, float su
         return sum;
     } else if constexpr (OP == OP_IPF) {
         // InnerProductCompressed::compute: scale * ip + offset (scalar.h:139-141).
-        return p.sq ? __fadd_rn(__fmul_rn(p.scale, sum), aux0) : sum;
+        // LVQ-8: the rows are stored mean-removed, so <q, x> = <q, y> + <q, mean> (aux0).
+        return p.sq ? __fadd_rn(__fmul_rn(p.scale, sum), aux0) : (p.lvq ? __fadd_rn(sum, aux0) : sum);
     } else if constexpr (OP == OP_COSF) {
         // cosine.h:334-335: sum / (sqrt(norm) * a_norm)
         return __fdiv_rn(sum, __fmul_rn(__fsqrt_rn(nrm), aux0));

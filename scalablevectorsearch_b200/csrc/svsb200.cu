@@ -65,6 +65,8 @@ struct svsb200_index {
     void* d_vectors = nullptr;
     uint32_t* d_graph = nullptr;
     uint16_t* d_ref_degree = nullptr;
+    float* d_mean = nullptr;          // LVQ-8: dataset mean
+    uint32_t lvq_const_offset = 0;
     size_t device_bytes = 0;
     // scratch, grown on demand
     DeviceBuffer<unsigned char> q_raw, q_codes, ids;
@@ -140,6 +142,8 @@ enum PrepMode : int {
     PREP_SQ_L2 = 2,   // EuclideanCompressed::fix_argument  (scalar.h:75-82)
     PREP_SQ_IP = 3,   // InnerProductCompressed::fix_argument (scalar.h:123-131)
     PREP_SQ_COS = 4,  // CosineSimilarityCompressed::fix_argument (scalar.h:168-171)
+    PREP_LVQ_L2 = 5,  // LVQ-8, L2: query with the dataset mean removed (own spec)
+    PREP_LVQ_IP = 6,  // LVQ-8, IP: raw query + <q, mean>
 };
 
 // Float16 -> float the way non-SIMD reference code does it (lib/float16.h:45-52):
@@ -163,7 +167,8 @@ template <int QT> __device__ __forceinline__ float q_scalar(const void* q, uint3
 template <int QT>
 __global__ void prepare_queries_kernel(const void* __restrict__ queries, uint32_t nq, uint32_t dim, uint32_t qstride,
                                        int mode, int metric, int code_type, float scale, float bias,
-                                       float* __restrict__ qf, uint8_t* __restrict__ qcodes, float* __restrict__ qaux) {
+                                       const float* __restrict__ mean, float* __restrict__ qf,
+                                       uint8_t* __restrict__ qcodes, float* __restrict__ qaux) {
     const uint32_t q = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (q >= nq) return;
@@ -176,8 +181,10 @@ __global__ void prepare_queries_kernel(const void* __restrict__ queries, uint32_
         float fv = 0.f;
         uint8_t cv = 0;
         if (i < dim) {
-            if (mode == PREP_FLOAT) {
+            if (mode == PREP_FLOAT || mode == PREP_LVQ_IP) {
                 fv = q_simd<QT>(src, i);
+            } else if (mode == PREP_LVQ_L2) {
+                fv = __fsub_rn(q_simd<QT>(src, i), mean[i]);
             } else if (mode == PREP_INT) {
                 if constexpr (QT == SVSB200_I8 || QT == SVSB200_U8) cv = static_cast<const uint8_t*>(src)[i];
             } else if (mode == PREP_SQ_L2) {
@@ -222,6 +229,10 @@ __global__ void prepare_queries_kernel(const void* __restrict__ queries, uint32_
             acc = __fadd_rn(acc, sq);
         }
         aux0 = __fsqrt_rn(acc);
+    } else if (mode == PREP_LVQ_IP) {
+        float acc = 0.f;
+        for (uint32_t i = 0; i < dim; ++i) acc = __fmaf_rn(f[i], mean[i], acc);
+        aux0 = acc;
     } else if (mode == PREP_SQ_IP) {
         // std::reduce over the fp32 query (libstdc++: four at a time, then the tail).
         float acc = 0.f;
@@ -281,14 +292,56 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ ids, const float*
     }
 }
 
+// LVQ-8 encoder (own specification), one warp per vector:
+//   r_i = x_i - mean_i;  lower = min r, upper = max r;  delta = (upper - lower) / 255
+//   {delta, lower} are stored as float16 (round to nearest even) and the codes are computed against
+//   the *stored* constants:  c_i = clamp(rint((r_i - lower16) / delta16), 0, 255)   (0 when delta16 == 0)
+// so that decode y_i = fma(delta16, c_i, lower16) is the nearest representable grid point.
+__global__ void lvq8_compress_kernel(const float* __restrict__ data, uint32_t n, uint32_t dim,
+                                     const float* __restrict__ mean, uint8_t* __restrict__ rows, uint32_t stride,
+                                     uint32_t const_offset) {
+    const uint32_t row = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n) return;
+    const float* x = data + size_t(row) * dim;
+    uint8_t* out = rows + size_t(row) * stride;
+    float lo = INFINITY, hi = -INFINITY;
+    for (uint32_t i = lane; i < dim; i += 32) {
+        const float r = __fsub_rn(x[i], mean[i]);
+        lo = fminf(lo, r);
+        hi = fmaxf(hi, r);
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = fminf(lo, __shfl_xor_sync(0xFFFFFFFFu, lo, o));
+        hi = fmaxf(hi, __shfl_xor_sync(0xFFFFFFFFu, hi, o));
+    }
+    const __half dh = __float2half_rn(__fdiv_rn(__fsub_rn(hi, lo), 255.0f));
+    const __half lh = __float2half_rn(lo);
+    const float d = __half2float(dh), l = __half2float(lh);
+    for (uint32_t i = lane; i < stride; i += 32) {
+        uint8_t c = 0;
+        if (i < dim && d > 0.0f) {
+            const float r = __fsub_rn(x[i], mean[i]);
+            float q = rintf(__fdiv_rn(__fsub_rn(r, l), d));
+            q = fminf(fmaxf(q, 0.0f), 255.0f);
+            c = uint8_t(int(q));
+        }
+        if (i < const_offset || i >= const_offset + 4) out[i] = c;
+    }
+    if (lane == 0) {
+        __half2 h = __halves2half2(dh, lh);
+        *reinterpret_cast<__half2*>(out + const_offset) = h;
+    }
+}
+
 template <int QT>
 static cudaError_t launch_prepare(const void* d_queries, uint32_t nq, uint32_t dim, uint32_t qstride, int mode, int metric,
-                                  int code_type, float scale, float bias, float* qf, uint8_t* qcodes, float* qaux,
-                                  cudaStream_t stream) {
+                                  int code_type, float scale, float bias, const float* mean, float* qf, uint8_t* qcodes,
+                                  float* qaux, cudaStream_t stream) {
     const int warps = 8;
     const unsigned grid = (nq + warps - 1) / warps;
     prepare_queries_kernel<QT><<<grid, warps * 32, 0, stream>>>(d_queries, nq, dim, qstride, mode, metric, code_type, scale,
-                                                               bias, qf, qcodes, qaux);
+                                                               bias, mean, qf, qcodes, qaux);
     count_launch();
     return cudaGetLastError();
 }
@@ -336,6 +389,11 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
     if (storage == SVSB200_SQ) {
         if (dtype != SVSB200_I8 && dtype != SVSB200_U8) return fail("svsb200_index_create: SQ codes must be int8/uint8");
         if (!aux) return fail("svsb200_index_create: SQ needs aux = {scale, bias}");
+    } else if (storage == SVSB200_LVQ8) {
+        if (dtype != SVSB200_U8) return fail("svsb200_index_create: LVQ-8 rows are uint8 codes (dtype SVSB200_U8)");
+        if (!aux) return fail("svsb200_index_create: LVQ-8 needs aux = mean[dim]");
+        if (row_stride_bytes != svsb200_lvq8_row_stride(dim))
+            return fail("svsb200_index_create: LVQ-8 rows must use svsb200_lvq8_row_stride(dim)");
     } else if (storage != SVSB200_PLAIN) {
         return fail("svsb200_index_create: unsupported storage kind");
     }
@@ -361,9 +419,13 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
         ix->scale = aux[0];
         ix->bias = aux[1];
     }
-    const size_t row_bytes = dim * esize(dtype);
+    size_t row_bytes = dim * esize(dtype);
+    if (storage == SVSB200_LVQ8) {
+        ix->lvq_const_offset = uint32_t(round_up(dim, 4));
+        row_bytes = ix->lvq_const_offset + 4;
+    }
     const size_t src_stride = row_stride_bytes ? row_stride_bytes : row_bytes;
-    ix->row_stride = uint32_t(round_up(row_bytes, 16));
+    ix->row_stride = uint32_t(storage == SVSB200_LVQ8 ? svsb200_lvq8_row_stride(dim) : round_up(row_bytes, 16));
     ix->gstride = uint32_t(round_up(ix->max_degree, 4));
 
     auto cleanup = [&](int rc) {
@@ -414,6 +476,10 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
             return cleanup(1);
         }
     }
+    if (storage == SVSB200_LVQ8) {
+        CUDA_TRY_IX(cudaMalloc(&ix->d_mean, dim * sizeof(float)));
+        CUDA_TRY_IX(cudaMemcpy(ix->d_mean, aux, dim * sizeof(float), cudaMemcpyHostToDevice));
+    }
     CUDA_TRY_IX(cudaMalloc(&ix->d_counter, sizeof(unsigned int)));
     CUDA_TRY_IX(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
     CUDA_TRY_IX(cudaEventCreate(&ix->ev_start));
@@ -430,6 +496,7 @@ int svsb200_index_destroy(svsb200_index* ix) {
     if (ix->d_graph) cudaFree(ix->d_graph);
     if (ix->d_ref_degree) cudaFree(ix->d_ref_degree);
     if (ix->d_counter) cudaFree(ix->d_counter);
+    if (ix->d_mean) cudaFree(ix->d_mean);
     ix->q_raw.release();
     ix->q_codes.release();
     ix->ids.release();
@@ -504,7 +571,12 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     // (euclidean.h:293-358) and the SQ CPOs (extensions/vamana/scalar.h:32-43).
     int op, mode;
     const int metric = ix->metric;
-    if (ix->storage == SVSB200_SQ) {
+    if (ix->storage == SVSB200_LVQ8) {
+        if (qdtype != SVSB200_F32 && qdtype != SVSB200_F16) return fail("LVQ-8 datasets take float32/float16 queries");
+        if (metric == SVSB200_COSINE) return fail("LVQ-8: cosine is not supported (L2 and MIP are)");
+        op = metric == SVSB200_L2 ? OP_L2F : OP_IPF;
+        mode = metric == SVSB200_L2 ? PREP_LVQ_L2 : PREP_LVQ_IP;
+    } else if (ix->storage == SVSB200_SQ) {
         if (qdtype != SVSB200_F32 && qdtype != SVSB200_F16) return fail("SQ datasets take float32/float16 queries");
         op = metric == SVSB200_L2 ? OP_L2I : metric == SVSB200_IP ? OP_IPF : OP_COSF;
         mode = metric == SVSB200_L2 ? PREP_SQ_L2 : metric == SVSB200_IP ? PREP_SQ_IP : PREP_SQ_COS;
@@ -534,19 +606,19 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     switch (qdtype) {
         case SVSB200_F32:
             err = launch_prepare<SVSB200_F32>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                              ix->scale, ix->bias, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                              ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
             break;
         case SVSB200_F16:
             err = launch_prepare<SVSB200_F16>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                              ix->scale, ix->bias, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                              ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
             break;
         case SVSB200_I8:
             err = launch_prepare<SVSB200_I8>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                             ix->scale, ix->bias, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                             ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
             break;
         default:
             err = launch_prepare<SVSB200_U8>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                             ix->scale, ix->bias, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                             ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
     }
     CUDA_TRY(err);
     CUDA_TRY(cudaMemsetAsync(ix->d_counter, 0, sizeof(unsigned int), stream));
@@ -562,6 +634,8 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.entry_point = ix->entry_point;
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
+    p.lvq = ix->storage == SVSB200_LVQ8;
+    p.lvq_const_offset = ix->lvq_const_offset;
     p.scale = ix->scale;
     p.bias = ix->bias;
     p.scale_sq = ix->scale * ix->scale;   // EuclideanCompressed ctor (scalar.h:68-72)
@@ -605,7 +679,8 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
 
     CUDA_TRY(cudaEventRecord(ix->ev_start, stream));
-    switch (ix->dtype) {
+    switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
+        case ROW_LVQ8: err = launch_search<ROW_LVQ8>(op, p, cfg, nrows); break;
         case SVSB200_F32: err = launch_search<SVSB200_F32>(op, p, cfg, nrows); break;
         case SVSB200_F16: err = launch_search<SVSB200_F16>(op, p, cfg, nrows); break;
         case SVSB200_I8: err = launch_search<SVSB200_I8>(op, p, cfg, nrows); break;
@@ -692,6 +767,37 @@ int svsb200_merge_topk_device(const uint64_t* d_ids, const float* d_dists, size_
         d_ids, d_dists, uint32_t(nshards), uint32_t(nq), uint32_t(k), metric != SVSB200_L2, d_out_ids, d_out_dists);
     count_launch();
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+size_t svsb200_lvq8_row_stride(size_t dim) { return round_up(round_up(dim, 4) + 4, 32); }
+
+int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows, int device) {
+    if (!data || !mean || !out_rows) return fail("svsb200_lvq8_compress: NULL argument");
+    if (n == 0 || dim == 0 || n >= (size_t(1) << 31)) return fail("svsb200_lvq8_compress: bad shape");
+    if (svsb200_device_count() == 0) return fail("svsb200_lvq8_compress: no CUDA device (there is no CPU fallback)");
+    CUDA_TRY(cudaSetDevice(device));
+    const size_t stride = svsb200_lvq8_row_stride(dim);
+    float *d_data = nullptr, *d_mean = nullptr;
+    uint8_t* d_rows = nullptr;
+    cudaError_t err = cudaMalloc(&d_data, n * dim * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&d_mean, dim * sizeof(float));
+    if (err == cudaSuccess) err = cudaMalloc(&d_rows, n * stride);
+    if (err == cudaSuccess) err = cudaMemcpy(d_data, data, n * dim * sizeof(float), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_mean, mean, dim * sizeof(float), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        const int warps = 8;
+        lvq8_compress_kernel<<<unsigned((n + warps - 1) / warps), warps * 32>>>(d_data, uint32_t(n), uint32_t(dim), d_mean,
+                                                                              d_rows, uint32_t(stride),
+                                                                              uint32_t(round_up(dim, 4)));
+        count_launch();
+        err = cudaGetLastError();
+    }
+    if (err == cudaSuccess) err = cudaMemcpy(out_rows, d_rows, n * stride, cudaMemcpyDeviceToHost);
+    if (d_data) cudaFree(d_data);
+    if (d_mean) cudaFree(d_mean);
+    if (d_rows) cudaFree(d_rows);
+    CUDA_TRY(err);
     return 0;
 }
 

@@ -41,7 +41,7 @@ class DataType(enum.Enum):
 
 
 _DTYPE_CODE = {np.dtype(np.float32): 0, np.dtype(np.float16): 1, np.dtype(np.int8): 2, np.dtype(np.uint8): 3}
-_STORAGE_PLAIN, _STORAGE_SQ = 0, 1
+_STORAGE_PLAIN, _STORAGE_SQ, _STORAGE_LVQ8 = 0, 1, 2
 
 
 @dataclass
@@ -114,6 +114,22 @@ def _read_entry_point(config_path: str) -> int:
     return int(m.group(1))
 
 
+def lvq8_compress(data: np.ndarray, mean: np.ndarray | None = None, device: int = 0):
+    """LVQ-8 encode float32 vectors on the GPU (own specification; stands where the
+    reference's closed ``LVQDataset<8>::compress(data, threadpool, padding)`` would).
+    Returns ``(rows uint8 [n, stride], mean float32 [dim])``."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    if mean is None:
+        mean = data.mean(axis=0, dtype=np.float64).astype(np.float32)
+    mean = np.ascontiguousarray(mean, dtype=np.float32)
+    lib = _lib.lib()
+    stride = lib.svsb200_lvq8_row_stride(data.shape[1])
+    rows = np.empty((data.shape[0], stride), dtype=np.uint8)
+    _lib.check(lib.svsb200_lvq8_compress(data.ctypes.data, data.shape[0], data.shape[1], mean.ctypes.data,
+                                         rows.ctypes.data, int(device)))
+    return rows, mean
+
+
 class Vamana:
     """GPU-backed static Vamana index exposing the reference's search surface."""
 
@@ -127,15 +143,16 @@ class Vamana:
     @classmethod
     def from_arrays(cls, data: np.ndarray, graph: np.ndarray, entry_point: int,
                     distance: DistanceType = DistanceType.L2, device: int = 0, sq: tuple | None = None,
-                    num_threads: int = 1) -> "Vamana":
+                    num_threads: int = 1, lvq8: tuple | None = None) -> "Vamana":
         """Assemble from in-memory parts: ``VamanaIndex(graph, data, entry_point, distance, threads)``
         (index/vamana/index.h:364-378).  ``graph`` is ``uint32[n][max_degree+1]``, degree first.
-        ``sq=(scale, bias)`` marks ``data`` as scalar-quantised int8/uint8 codes."""
+        ``sq=(scale, bias)`` marks ``data`` as scalar-quantised int8/uint8 codes;
+        ``lvq8=(dim, mean)`` marks ``data`` as LVQ-8 rows from :func:`lvq8_compress`."""
         self = cls.__new__(cls)
-        self._init(data, graph, entry_point, distance, device, num_threads, sq)
+        self._init(data, graph, entry_point, distance, device, num_threads, sq, lvq8)
         return self
 
-    def _init(self, data, graph, entry_point, distance, device, num_threads, sq=None):
+    def _init(self, data, graph, entry_point, distance, device, num_threads, sq=None, lvq8=None):
         data = np.ascontiguousarray(data)
         graph = np.ascontiguousarray(graph, dtype=np.uint32)
         if data.ndim != 2 or graph.ndim != 2:
@@ -152,11 +169,16 @@ class Vamana:
         handle = C.c_void_p()
         aux = None
         storage = _STORAGE_PLAIN
+        dim, stride = data.shape[1], 0
         if sq is not None:
             aux = (C.c_float * 2)(float(sq[0]), float(sq[1]))
             storage = _STORAGE_SQ
+        if lvq8 is not None:
+            dim, mean = int(lvq8[0]), np.ascontiguousarray(lvq8[1], dtype=np.float32)
+            aux = (C.c_float * dim)(*mean.tolist())
+            storage, stride = _STORAGE_LVQ8, data.shape[1]
         _lib.check(self._lib.svsb200_index_create(
-            data.ctypes.data, _DTYPE_CODE[data.dtype], data.shape[0], data.shape[1], 0, graph.ctypes.data,
+            data.ctypes.data, _DTYPE_CODE[data.dtype], data.shape[0], dim, stride, graph.ctypes.data,
             graph.shape[1], int(entry_point), int(self._distance), storage,
             C.cast(aux, C.c_void_p) if aux is not None else None, int(device), C.byref(handle)))
         self._h = handle

@@ -181,3 +181,33 @@ def test_cpp_adapter_cli_matches_python_path(dataset, ref_outputs, tmp_path):
     assert "GpuVamanaIndex" in out.stdout
     ids = io.read_vecs(str(tmp_path / "res_idx.ivecs"))
     assert np.array_equal(ids.astype(np.uint32), ref_outputs["l2_f32_f32_w15_c15_ids"])
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip"])
+@pytest.mark.parametrize("dim", [96, 100])
+def test_lvq8_fused_decompress_distance_vs_oracle(oracle, metric, dim):
+    """LVQ-8 (own specification -- the reference's LVQ is closed source, parity with Intel's binary is
+    UNPINNED): GPU encoder bytes == oracle encoder bytes, fused decompress+distance search == oracle,
+    and the compressed search keeps recall close to the uncompressed one."""
+    from scalablevectorsearch_b200 import lvq8_compress
+    rng = np.random.default_rng(dim)
+    n = 3000
+    centres = rng.standard_normal((20, dim)).astype(np.float32)
+    x = (centres[rng.integers(0, 20, n)] + 0.3 * rng.standard_normal((n, dim))).astype(np.float32)
+    q = (centres[rng.integers(0, 20, 300)] + 0.3 * rng.standard_normal((300, dim))).astype(np.float32)
+    graph = knn_graph(x, 32, rng)
+    rows, mean = lvq8_compress(x)
+    want_rows = oracle.lvq8_compress(x, mean)
+    assert np.array_equal(rows, want_rows), "LVQ-8 encoder bytes differ from the oracle"
+    index = make_index(rows, graph, 7, metric, lvq8=(dim, mean))
+    want = oracle.lvq8_index(rows, dim, mean, graph, 7, metric)
+    for qq in (q, q.astype(np.float16)):
+        for window, cap in ((8, 8), (32, 48)):
+            got = search(index, qq, 8, window, cap)
+            wi, wd = want.search(qq, 8, window, cap)
+            assert_same(got, wi, wd, f"lvq8 {metric} d{dim} {qq.dtype} w{window}")
+    # recall of the compressed index vs the exact index on the same graph (scalar_search.cpp uses eps 0.008)
+    exact = search(make_index(x, graph, 7, metric), q, 8, 32, 48)[0]
+    comp = search(index, q, 8, 32, 48)[0]
+    overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) for a, b in zip(exact, comp)]) / 8
+    assert overlap > 0.93, overlap
