@@ -9,14 +9,17 @@
 //
 //     search(QueryResultView<I>, queries, VamanaSearchParameters, cancel)   (index.h:564-611)
 //
-// is replaced.  Because `ManagerImpl::search` calls `impl().search(...)` on the static type
-// (`manager.h:141-166` -> `index/index.h:44-55`), wrapping it with the reference's own factory
+// is replaced.  `ManagerImpl::search` calls `impl().search(...)` on the static type
+// (`manager.h:141-166` -> `index/index.h:44-55`), so type-erasing it with the reference's own
+// `VamanaImpl` / `svs::Vamana` (`orchestrators/vamana.h:108-276,293-305`)
 //
-//     svs::Vamana v = svs::make_vamana<svs::lib::Types<float>>(
+//     svs::Vamana v = svsb200::make_gpu_vamana<svs::lib::Types<float>>(
 //         svsb200::GpuVamanaIndex{std::move(cpu_index), /*device=*/0});
 //
-// yields a stock type-erased `svs::Vamana` whose `search` runs on the GPU -- the object that
-// `utils/search_index.cpp`, `bindings/python` and `bindings/cpp` hold.
+// yields a stock `svs::Vamana` whose `search` runs on the GPU -- the object that
+// `utils/search_index.cpp`, `bindings/python` and `bindings/cpp` hold.  (`svs::make_vamana`
+// itself cannot be used: it re-deduces `VamanaIndex{args...}` and would slice to the CPU base,
+// `orchestrators/vamana.h:711-715`.)
 //
 // This header compiles against the reference headers (`-I<reference>/include`); it contains
 // no reference code.  Errors from the C ABI are rethrown as svs::ANNException
@@ -24,6 +27,7 @@
 #pragma once
 
 #include "svs/index/vamana/index.h"
+#include "svs/orchestrators/vamana.h"
 #include "svs/quantization/scalar/scalar.h"
 
 #include "svsb200.h"
@@ -175,5 +179,12 @@ GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&, int)
 template <typename Graph, typename Data, typename Dist>
 GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&)
     -> GpuVamanaIndex<Graph, Data, Dist>;
+
+/// Type-erase a GpuVamanaIndex into the reference's orchestrator object.
+template <svs::lib::TypeList QueryTypes, typename Graph, typename Data, typename Dist>
+svs::Vamana make_gpu_vamana(GpuVamanaIndex<Graph, Data, Dist>&& index) {
+    using Impl = GpuVamanaIndex<Graph, Data, Dist>;
+    return svs::Vamana{std::make_unique<svs::VamanaImpl<QueryTypes, Impl>>(std::move(index))};
+}
 
 } // namespace svsb200

@@ -2,8 +2,8 @@
 // index handed to the orchestrator is a svsb200::GpuVamanaIndex.  Same positional arguments,
 // same output file (`<prefix>_idx.ivecs`), so BASELINE config #1 (data/test_dataset through
 // the CLI) runs unchanged.  Everything except GpuVamanaIndex is the reference's public API:
-// svs::index::vamana::auto_assemble (index/vamana/index.h:1022-1046), svs::make_vamana
-// (orchestrators/vamana.h:711-740), svs::load_data, QueryResult::save_vecs.
+// svs::index::vamana::auto_assemble (index/vamana/index.h:1022-1046), svs::VamanaImpl / svs::Vamana
+// (orchestrators/vamana.h:108-305), svs::load_data, QueryResult::save_vecs.
 #include "gpu_vamana_index.h"
 
 #include "svs/core/distance.h"
@@ -36,7 +36,7 @@ void run(
         Dist{},
         threads
     );
-    auto index = svs::make_vamana<svs::lib::Types<Eq>>(svsb200::GpuVamanaIndex{std::move(cpu), device});
+    auto index = svsb200::make_gpu_vamana<svs::lib::Types<Eq>>(svsb200::GpuVamanaIndex{std::move(cpu), device});
     index.set_search_parameters(index.get_search_parameters().buffer_config({window}));
     const auto queries = svs::load_data<Eq>(query_file);
     auto tic = svs::lib::now();
