@@ -212,6 +212,9 @@ def run_ours(args):
     w, base, queries, graph, ep = load_workload(args.workload, rank, world, barrier)
     if args.window:
         w = dict(w, window=args.window)
+    if args.batch:
+        w = dict(w, nq=args.batch)
+        queries = queries[:args.batch]
     metric = {"l2": DistanceType.L2, "ip": DistanceType.MIP, "cosine": DistanceType.Cosine}[w["metric"]]
     index = Vamana.from_arrays(base, graph, ep, metric, device=local_rank)
     index.search_parameters.buffer_config = SearchBufferConfig(w["window"])
@@ -397,6 +400,7 @@ def main():
     ap.add_argument("--workload", default=os.environ.get("SVSB200_WORKLOAD", "c2-1Mx96-f32-L2-w128"),
                     choices=sorted(WORKLOADS))
     ap.add_argument("--window", type=int, default=0)
+    ap.add_argument("--batch", type=int, default=0, help="use only the first BATCH queries (experiments)")
     ap.add_argument("--warps-per-cta", dest="warps_per_cta", type=int, default=0)
     ap.add_argument("--ctas-per-sm", dest="ctas_per_sm", type=int, default=0)
     ap.add_argument("--rows-in-flight", dest="rows_in_flight", type=int, default=0)

@@ -80,8 +80,9 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap
                                                   uint32_t filter_bytes) {
     // query (fp32 or bytes, reserve fp32) + buffer keys/ids + candidate keys/ids +
     // survivor keys/pos/ids/final-pos + visited filter
+    // + two staged adjacency rows
     return size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 + size_t(deg_pad) * 16 +
-           size_t(filter_bytes);
+           size_t(filter_bytes) + size_t(deg_pad) * 8;
 }
 
 // One launcher per (row type, op); defined in search_<type>.cu.
