@@ -383,7 +383,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ---------------------------------------------------------------------------------------
 template <int ROWT, int OP, int DS, int NROWS>
 #ifndef SVSB200_ADAPTIVE
-#define SVSB200_ADAPTIVE 1
+#define SVSB200_ADAPTIVE 0   // measured: the extra single-row pass costs more (code size, spills) than it saves
 #endif
 #ifndef SVSB200_STAGE_ADJ
 #define SVSB200_STAGE_ADJ 1
