@@ -56,7 +56,6 @@ struct SearchParams {
     uint32_t filter_slots;     // per-query exact visited filter (power of two, 0 = off)
     uint32_t filter_shift;     // log2(filter_slots)
     uint32_t filter_tag16;     // 1: entries are 16-bit tags id >> filter_shift (exact while n <= slots * 65535)
-    uint32_t prefetch_adj;     // L2-prefetch the adjacency rows of the next P unvisited buffer entries
     // outputs
     void* out_ids;
     int id_bytes;

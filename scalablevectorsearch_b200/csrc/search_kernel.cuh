@@ -498,18 +498,6 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
                 for (uint32_t i = lane * 4; i < p.gstride; i += 128) cp_async16(dst + i, src + i);
                 cp_async_commit();
             }
-            if (p.prefetch_adj) {
-                // The entries right behind the chosen one are the likeliest next expansions:
-                // pull their adjacency rows towards L2 now (a wasted prefetch costs one row).
-                const uint32_t j = pos + 1 + lane;
-                if (lane < p.prefetch_adj && j < upper) {
-                    const uint32_t e = bid[j];
-                    if (!(e & kVisitedBit)) {
-                        const char* a = reinterpret_cast<const char*>(p.graph + size_t(e) * p.gstride);
-                        for (uint32_t off = 0; off < p.gstride * 4; off += 128) prefetch_l2(a + off);
-                    }
-                }
-            }
             __syncwarp();
             if (lane == 0) bid[pos] = node | kVisitedBit;
             cursor = pos + 1;

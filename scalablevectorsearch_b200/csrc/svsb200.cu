@@ -79,7 +79,7 @@ struct svsb200_index {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     // options
-    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, prefetch_adj = -1, filter_tag16 = 1;
+    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1;
     std::mutex mutex;
 };
 
@@ -539,9 +539,6 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
         ix->rows_in_flight = value;
     } else if (key == "filter_tag16") {
         ix->filter_tag16 = value;
-    } else if (key == "prefetch_adj") {
-        if (value > 32) return fail("prefetch_adj must be <= 32");
-        ix->prefetch_adj = value;
     } else if (key == "visited_filter_slots") {
         // -1 = default; 0 = off; otherwise a power of two
         if (value > 0 && (value & (value - 1))) return fail("visited_filter_slots must be a power of two");
@@ -661,7 +658,6 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     while ((1u << p.filter_shift) < p.filter_slots) ++p.filter_shift;
     // 16-bit tags are exact as long as every id >> shift fits below the 0xFFFF "empty" mark
     p.filter_tag16 = p.filter_slots && ((uint64_t(ix->n - 1) >> p.filter_shift) < 0xFFFFull) && ix->filter_tag16 != 0;
-    p.prefetch_adj = ix->prefetch_adj < 0 ? 4u : uint32_t(ix->prefetch_adj);
 
     LaunchConfig cfg{};
     const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
