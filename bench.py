@@ -333,15 +333,16 @@ def run_ours(args):
         ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(ncu_path) and world == 1:
             ncu_traffic = json.load(open(ncu_path)).get(args.workload, {}).get("dram_bytes_per_launch")
-        # recall@10 on a sample against exact brute force (torch matmul: harness only)
+        # recall@10 on a sample against the exact top-k (svsb200_exhaustive_device: same distance code, ties by id)
         sample = min(1000, nq)
-        xb = torch.from_numpy(base).to(dev)
-        qs = q_dev[:sample]
-        d2 = (xb * xb).sum(1)[None, :] - 2.0 * qs @ xb.T
-        gt = d2.topk(k, largest=False).indices.cpu().numpy()
+        gt_ids = torch.empty((sample, k), dtype=torch.int64, device=dev)
+        gt_d = torch.empty((sample, k), dtype=torch.float32, device=dev)
+        index.exhaustive_device(q_dev.data_ptr(), queries.dtype, sample, k, gt_ids.data_ptr(), gt_d.data_ptr(),
+                                stream=torch.cuda.current_stream(dev).cuda_stream or 1)
+        torch.cuda.synchronize()
+        gt = gt_ids.cpu().numpy()
         got = ids_all[:sample].cpu().numpy()
         recall = float(np.mean([len(set(got[i]) & set(gt[i])) for i in range(sample)])) / k
-        del xb, d2
 
         cpu = None
         if not args.no_cpu_baseline:

@@ -86,6 +86,8 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap
 
 // One launcher per (row type, op); defined in search_<type>.cu.
 template <int ROWT> cudaError_t launch_search(int op, const SearchParams& p, const LaunchConfig& cfg, int rows_in_flight);
+// Exhaustive scan with the same distance code (ground truth / flat search).
+template <int ROWT> cudaError_t launch_search_exhaustive(int op, const SearchParams& p, const LaunchConfig& cfg);
 
 void count_launch();
 

@@ -12,4 +12,13 @@ template <> cudaError_t launch_search<SVSB200_F16>(int op, const SearchParams& p
     }
 }
 
+template <> cudaError_t launch_search_exhaustive<SVSB200_F16>(int op, const SearchParams& p, const LaunchConfig& cfg) {
+    switch (op) {
+        case OP_L2F: return launch_exhaustive<SVSB200_F16, OP_L2F>(p, cfg);
+        case OP_IPF: return launch_exhaustive<SVSB200_F16, OP_IPF>(p, cfg);
+        case OP_COSF: return launch_exhaustive<SVSB200_F16, OP_COSF>(p, cfg);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace svsb200

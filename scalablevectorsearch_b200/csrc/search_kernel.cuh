@@ -381,7 +381,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ---------------------------------------------------------------------------------------
 // The kernel.
 // ---------------------------------------------------------------------------------------
-template <int ROWT, int OP, int DS, int NROWS>
 #ifndef SVSB200_ADAPTIVE
 #define SVSB200_ADAPTIVE 0   // measured: the extra single-row pass costs more (code size, spills) than it saves
 #endif
@@ -391,6 +390,11 @@ template <int ROWT, int OP, int DS, int NROWS>
 #ifndef SVSB200_MIN_BLOCKS
 #define SVSB200_MIN_BLOCKS 2   // <= 128 registers: four 4-warp CTAs (16 warps) per SM
 #endif
+// EXH = true turns the same machinery into an exhaustive scan (the reference's flat index,
+// index/flat/flat.h:159,421-465, used here for ground truth): the "neighbours" of every step
+// are the next block of consecutive ids, there is no visited filter and no expansion order;
+// the sorted buffer (window = capacity = k) ends up holding the exact top-k, ties by id.
+template <int ROWT, int OP, int DS, int NROWS, bool EXH = false>
 __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(const __grid_constant__ SearchParams p) {
     constexpr bool kInt = (OP >= OP_L2I);
     constexpr int G = kInt ? 4 : 16 / Row<ROWT>::LPT;     // threads per row
@@ -445,99 +449,111 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
         __syncwarp();
 
         // ---- EntryPointInitializer (greedy_search.h:62-94): clear, push entry point ----
-        uint32_t size = 1, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
-        if (lane == 0) cid[0] = p.entry_point;
-        __syncwarp();
-        eval_pass<ROWT, OP, DS, 1>(p, q_s, vectors, cid, ckey, 0, 1, g, t, aux0, aux1, ksign);
-        __syncwarp();
-        if (lane == 0) {
-            bkey[0] = ckey[0];
-            bid[0] = p.entry_point;
+        uint32_t size = EXH ? 0 : 1, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
+        if constexpr (!EXH) {
+            if (lane == 0) cid[0] = p.entry_point;
+            __syncwarp();
+            eval_pass<ROWT, OP, DS, 1>(p, q_s, vectors, cid, ckey, 0, 1, g, t, aux0, aux1, ksign);
+            __syncwarp();
+            if (lane == 0) {
+                bkey[0] = ckey[0];
+                bid[0] = p.entry_point;
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        uint32_t scan_base = 0;   // EXH: first id of the current block
         uint32_t staged_node = kNoNeighbor;   // node whose adjacency row sits in adj[staged_buf]
         uint32_t staged_buf = 0;
 
         // ---- main loop: while (!buffer.done()) (greedy_search.h:153) ----
         for (;;) {
-            // buffer.next(): first unvisited entry inside min(size, window)
-            const uint32_t upper = min(size, W);
-            uint32_t pos = cursor, pred_pos = 0xFFFFFFFFu;
-            bool found = false;
-            while (pos < upper) {
-                uint32_t j = pos + lane;
-                bool unv = (j < upper) && !(bid[j] & kVisitedBit);
-                unsigned m = __ballot_sync(FULL, unv);
-                if (m) {
-                    // Once the first few hops are over, the unvisited entry right behind the
-                    // chosen one is the next node to be expanded in 97% of hops (measured).
-                    const unsigned m2 = m & (m - 1);
-                    if (m2) pred_pos = pos + __ffs(m2) - 1;
-                    pos += __ffs(m) - 1;
-                    found = true;
-                    break;
-                }
-                pos += 32;
-            }
-            if (!found) break;   // done()
-            const uint32_t node = bid[pos];
-            // Adjacency row of this node: staged by the previous hop if the prediction held.
-            const bool have_adj = (node == staged_node);
-            const uint32_t* adj_cur = adj + staged_buf * p.deg_pad;
-            // (always drain: a stale copy from a missed prediction must not land later)
-            cp_async_wait_all();
-            __syncwarp();
-            // Stage the predicted next node's adjacency row (asynchronous global->shared copy,
-            // in flight during this hop's distance evaluations and merge).
-            staged_node = kNoNeighbor;
-            if (SVSB200_STAGE_ADJ && pred_pos != 0xFFFFFFFFu) {
-                staged_node = bid[pred_pos] & kIdMask;
-                staged_buf ^= 1u;
-                uint32_t* dst = adj + staged_buf * p.deg_pad;
-                const uint32_t* src = p.graph + size_t(staged_node) * p.gstride;
-                for (uint32_t i = lane * 4; i < p.gstride; i += 128) cp_async16(dst + i, src + i);
-                cp_async_commit();
-            }
-            __syncwarp();
-            if (lane == 0) bid[pos] = node | kVisitedBit;
-            cursor = pos + 1;
-
-            // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding.
-            // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
-            const uint32_t* grow = p.graph + size_t(node) * p.gstride;
-            const uint32_t fmask = p.filter_slots - 1;
-            uint32_t deg = 0, ncand = 0;
-            for (uint32_t j0 = 0; j0 < p.gstride; j0 += 32) {
-                uint32_t j = j0 + lane;
-                uint32_t nb = (j < p.gstride) ? (have_adj ? adj_cur[j] : __ldg(grow + j)) : kNoNeighbor;
-                bool fresh = nb != kNoNeighbor;
-                deg += __popc(__ballot_sync(FULL, fresh));
-                if (p.filter_slots && fresh) {
-                    // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember
-                    const uint32_t slot = nb & fmask;
-                    if (p.filter_tag16) {
-                        // slot index + 16-bit tag reconstruct the full id: still exact
-                        const uint16_t tag = uint16_t(nb >> p.filter_shift);
-                        fresh = filt16[slot] != tag;
-                        if (fresh) filt16[slot] = tag;
-                    } else {
-                        fresh = filt[slot] != nb;
-                        if (fresh) filt[slot] = nb;
-                    }
-                }
-                const unsigned m = __ballot_sync(FULL, fresh);
-                if (fresh) cid[ncand + __popc(m & ((1u << lane) - 1u))] = nb;
-                ncand += __popc(m);
+            uint32_t deg = 0;
+            if constexpr (EXH) {
+                if (scan_base >= p.n) break;
+                deg = min(p.deg_pad, p.n - scan_base);
+                for (uint32_t i = lane; i < deg; i += 32) cid[i] = scan_base + i;
+                scan_base += deg;
                 __syncwarp();
-            }
-            ++n_hops;
-            // tracker.visited(node, neighbors.size()) (greedy_search.h:165) counts the row as
-            // the reference stores it, i.e. including the repeated ids removed at upload.
-            n_evals += p.hops ? uint32_t(__ldg(p.ref_degree + node)) : deg;
-            n_fetched += ncand;
-            if (ncand == 0) continue;
-            deg = ncand;   // from here on: the candidates that are actually evaluated
+            } else {
+                // buffer.next(): first unvisited entry inside min(size, window)
+                const uint32_t upper = min(size, W);
+                uint32_t pos = cursor, pred_pos = 0xFFFFFFFFu;
+                bool found = false;
+                while (pos < upper) {
+                    uint32_t j = pos + lane;
+                    bool unv = (j < upper) && !(bid[j] & kVisitedBit);
+                    unsigned m = __ballot_sync(FULL, unv);
+                    if (m) {
+                        // Once the first few hops are over, the unvisited entry right behind the
+                        // chosen one is the next node to be expanded in 97% of hops (measured).
+                        const unsigned m2 = m & (m - 1);
+                        if (m2) pred_pos = pos + __ffs(m2) - 1;
+                        pos += __ffs(m) - 1;
+                        found = true;
+                        break;
+                    }
+                    pos += 32;
+                }
+                if (!found) break;   // done()
+                const uint32_t node = bid[pos];
+                // Adjacency row of this node: staged by the previous hop if the prediction held.
+                const bool have_adj = (node == staged_node);
+                const uint32_t* adj_cur = adj + staged_buf * p.deg_pad;
+                // (always drain: a stale copy from a missed prediction must not land later)
+                cp_async_wait_all();
+                __syncwarp();
+                // Stage the predicted next node's adjacency row (asynchronous global->shared copy,
+                // in flight during this hop's distance evaluations and merge).
+                staged_node = kNoNeighbor;
+                if (SVSB200_STAGE_ADJ && pred_pos != 0xFFFFFFFFu) {
+                    staged_node = bid[pred_pos] & kIdMask;
+                    staged_buf ^= 1u;
+                    uint32_t* dst = adj + staged_buf * p.deg_pad;
+                    const uint32_t* src = p.graph + size_t(staged_node) * p.gstride;
+                    for (uint32_t i = lane * 4; i < p.gstride; i += 128) cp_async16(dst + i, src + i);
+                    cp_async_commit();
+                }
+                __syncwarp();
+                if (lane == 0) bid[pos] = node | kVisitedBit;
+                cursor = pos + 1;
 
+                // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding.
+                // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
+                const uint32_t* grow = p.graph + size_t(node) * p.gstride;
+                const uint32_t fmask = p.filter_slots - 1;
+                uint32_t ncand = 0;
+                for (uint32_t j0 = 0; j0 < p.gstride; j0 += 32) {
+                    uint32_t j = j0 + lane;
+                    uint32_t nb = (j < p.gstride) ? (have_adj ? adj_cur[j] : __ldg(grow + j)) : kNoNeighbor;
+                    bool fresh = nb != kNoNeighbor;
+                    deg += __popc(__ballot_sync(FULL, fresh));
+                    if (p.filter_slots && fresh) {
+                        // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember
+                        const uint32_t slot = nb & fmask;
+                        if (p.filter_tag16) {
+                            // slot index + 16-bit tag reconstruct the full id: still exact
+                            const uint16_t tag = uint16_t(nb >> p.filter_shift);
+                            fresh = filt16[slot] != tag;
+                            if (fresh) filt16[slot] = tag;
+                        } else {
+                            fresh = filt[slot] != nb;
+                            if (fresh) filt[slot] = nb;
+                        }
+                    }
+                    const unsigned m = __ballot_sync(FULL, fresh);
+                    if (fresh) cid[ncand + __popc(m & ((1u << lane) - 1u))] = nb;
+                    ncand += __popc(m);
+                    __syncwarp();
+                }
+                ++n_hops;
+                // tracker.visited(node, neighbors.size()) (greedy_search.h:165) counts the row as
+                // the reference stores it, i.e. including the repeated ids removed at upload.
+                n_evals += p.hops ? uint32_t(__ldg(p.ref_degree + node)) : deg;
+                n_fetched += ncand;
+                if (ncand == 0) continue;
+                deg = ncand;   // from here on: the candidates that are actually evaluated
+
+            }
             // neighbour expansion: distance of every neighbour (greedy_search.h:190-201).
             // A pass covers NROWS x GROUPS candidates; a remainder that fits one row per group
             // takes the single-row pass (half the instructions).
@@ -554,7 +570,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
 
             // ---- merge the candidates into the sorted buffer (== sequential insert) ----
             const bool full = (size == C);
-            const float backkey = bkey[size - 1];
+            const float backkey = size ? bkey[size - 1] : 0.0f;
             uint32_t S = 0, minpos = 0xFFFFFFFFu;
             for (uint32_t r0 = 0; r0 < deg; r0 += 32) {
                 const uint32_t r = r0 + lane;
@@ -674,6 +690,21 @@ cudaError_t launch_one(const SearchParams& p, const LaunchConfig& cfg) {
         if (err != cudaSuccess) return err;
         grid = -grid * (resident > 0 ? resident : 1);
     }
+    const int needed = int((p.nq + cfg.warps_per_cta - 1) / cfg.warps_per_cta);
+    if (grid > needed) grid = needed;
+    kernel<<<grid, cfg.warps_per_cta * 32, cfg.smem_bytes, cfg.stream>>>(p);
+    count_launch();
+    return cudaGetLastError();
+}
+
+template <int ROWT, int OP> cudaError_t launch_exhaustive(const SearchParams& p, const LaunchConfig& cfg) {
+    auto kernel = vamana_search_kernel<ROWT, OP, 0, 2, true>;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
+    if (err != cudaSuccess) return err;
+    int resident = 0;
+    err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, cfg.warps_per_cta * 32, cfg.smem_bytes);
+    if (err != cudaSuccess) return err;
+    int grid = -cfg.grid * (resident > 0 ? resident : 1);
     const int needed = int((p.nq + cfg.warps_per_cta - 1) / cfg.warps_per_cta);
     if (grid > needed) grid = needed;
     kernel<<<grid, cfg.warps_per_cta * 32, cfg.smem_bytes, cfg.stream>>>(p);

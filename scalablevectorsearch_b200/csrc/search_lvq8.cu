@@ -11,4 +11,12 @@ template <> cudaError_t launch_search<ROW_LVQ8>(int op, const SearchParams& p, c
     }
 }
 
+template <> cudaError_t launch_search_exhaustive<ROW_LVQ8>(int op, const SearchParams& p, const LaunchConfig& cfg) {
+    switch (op) {
+        case OP_L2F: return launch_exhaustive<ROW_LVQ8, OP_L2F>(p, cfg);
+        case OP_IPF: return launch_exhaustive<ROW_LVQ8, OP_IPF>(p, cfg);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
 }  // namespace svsb200

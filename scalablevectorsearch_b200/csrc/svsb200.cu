@@ -552,7 +552,8 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
 
 // Shared body of svsb200_search / svsb200_search_device: everything on the device.
 static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
-                            size_t capacity, void* d_out_ids, int id_bytes, float* d_out_dists, cudaStream_t stream) {
+                            size_t capacity, void* d_out_ids, int id_bytes, float* d_out_dists, cudaStream_t stream,
+                            bool exhaustive = false) {
     if (id_bytes != 4 && id_bytes != 8) return fail("id_bytes must be 4 or 8");
     if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
     if (window > capacity) {
@@ -653,7 +654,7 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.hops = ix->counting ? ix->hops.ptr : nullptr;
     p.evals = ix->counting ? ix->evals.ptr : nullptr;
     p.fetched = ix->counting ? ix->fetched.ptr : nullptr;
-    p.filter_slots = ix->filter_slots < 0 ? 4096u : uint32_t(ix->filter_slots);
+    p.filter_slots = exhaustive ? 0u : (ix->filter_slots < 0 ? 4096u : uint32_t(ix->filter_slots));
     p.filter_shift = 0;
     while ((1u << p.filter_shift) < p.filter_slots) ++p.filter_shift;
     // 16-bit tags are exact as long as every id >> shift fits below the 0xFFFF "empty" mark
@@ -671,10 +672,23 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     // grid: persistent CTAs; the launcher clamps to what is resident.  ctas_per_sm == 0
     // means "as many as fit" (computed by the launcher through the occupancy API).
     cfg.grid = ix->sm_count * (ix->ctas_per_sm ? int(ix->ctas_per_sm) : 0);
-    if (cfg.grid == 0) cfg.grid = -ix->sm_count;   // negative: launcher multiplies by occupancy
+    if (cfg.grid == 0 || exhaustive) cfg.grid = -ix->sm_count;   // negative: launcher multiplies by occupancy
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
 
     CUDA_TRY(cudaEventRecord(ix->ev_start, stream));
+    if (exhaustive) {
+        switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
+            case ROW_LVQ8: err = launch_search_exhaustive<ROW_LVQ8>(op, p, cfg); break;
+            case SVSB200_F32: err = launch_search_exhaustive<SVSB200_F32>(op, p, cfg); break;
+            case SVSB200_F16: err = launch_search_exhaustive<SVSB200_F16>(op, p, cfg); break;
+            case SVSB200_I8: err = launch_search_exhaustive<SVSB200_I8>(op, p, cfg); break;
+            default: err = launch_search_exhaustive<SVSB200_U8>(op, p, cfg);
+        }
+        CUDA_TRY(err);
+        CUDA_TRY(cudaEventRecord(ix->ev_stop, stream));
+        ix->timed = true;
+        return 0;
+    }
     switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
         case ROW_LVQ8: err = launch_search<ROW_LVQ8>(op, p, cfg, nrows); break;
         case SVSB200_F32: err = launch_search<SVSB200_F32>(op, p, cfg, nrows); break;
@@ -797,8 +811,15 @@ int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* 
     return 0;
 }
 
-int svsb200_exhaustive_device(svsb200_index*, const void*, int, size_t, size_t, uint64_t*, float*, void*) {
-    return fail("svsb200_exhaustive_device: not built in this revision");
+int svsb200_exhaustive_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, uint64_t* d_out_ids,
+                              float* d_out_dists, void* stream) {
+    if (!ix) return fail("svsb200_exhaustive_device: NULL index");
+    if (nq && (!d_queries || !d_out_ids || !d_out_dists)) return fail("svsb200_exhaustive_device: NULL buffer");
+    if (k == 0 || k > 1024) return fail("svsb200_exhaustive_device: k must be in [1, 1024]");
+    std::lock_guard<std::mutex> lock(ix->mutex);
+    CUDA_TRY(cudaSetDevice(ix->device));
+    return search_on_device(ix, d_queries, qdtype, nq, k, k, k, d_out_ids, 8, d_out_dists,
+                            stream ? static_cast<cudaStream_t>(stream) : ix->own_stream, true);
 }
 
 }  // extern "C"

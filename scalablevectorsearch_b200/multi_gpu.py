@@ -70,8 +70,14 @@ class ReplicatedSearch:
         nq = queries.shape[0]
         start, stop = balance(nq, world, rank)
         ids, dists = self.local_search(queries[start:stop], k)
+        if world == 1:
+            return ids, dists
         counts = [balance(nq, world, r)[1] - balance(nq, world, r)[0] for r in range(world)]
-        return _gather_rows(ids, counts, self.group), _gather_rows(dists, counts, self.group)
+        # one collective for both result arrays: ids and the float32 distances (bit-cast, widened to
+        # int64 lanes) travel as a single [rows, 2k] int64 block -- the gather is latency bound
+        packed = torch.cat([ids, dists.view(torch.int32).to(torch.int64)], dim=1)
+        out = _gather_rows(packed, counts, self.group)
+        return out[:, :k].contiguous(), out[:, k:].to(torch.int32).view(torch.float32)
 
 
 def merge_topk_reference_order(ids: np.ndarray, dists: np.ndarray, k: int, greater: bool):

@@ -260,6 +260,13 @@ class Vamana:
             cfg.search_buffer_capacity, int(self._params.search_buffer_visited_set), d_ids, id_bytes, d_dists,
             stream or None))
 
+    def exhaustive_device(self, d_queries: int, qdtype: np.dtype, nq: int, n_neighbors: int, d_ids: int, d_dists: int,
+                          stream: int = 0):
+        """Exact top-k of every query against all base vectors (same distance code; ties by id) -- the
+        harness's ground truth, standing where the reference uses ``svs::Flat`` (index/flat/flat.h:159)."""
+        _lib.check(self._lib.svsb200_exhaustive_device(self._h, d_queries, _DTYPE_CODE[np.dtype(qdtype)], nq,
+                                                       int(n_neighbors), d_ids, d_dists, stream or None))
+
     # ---- instrumentation ---------------------------------------------------------------
     def set_counting(self, enabled: bool):
         _lib.check(self._lib.svsb200_set_counting(self._h, int(enabled)))

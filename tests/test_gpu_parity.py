@@ -211,3 +211,29 @@ def test_lvq8_fused_decompress_distance_vs_oracle(oracle, metric, dim):
     comp = search(index, q, 8, 32, 48)[0]
     overlap = np.mean([len(set(a.tolist()) & set(b.tolist())) for a, b in zip(exact, comp)]) / 8
     assert overlap > 0.93, overlap
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_exhaustive_scan_is_exact_topk(oracle, metric):
+    """svsb200_exhaustive_device: top-k over all base vectors with the search path's own distance code,
+    ties broken by id -- checked against oracle distances sorted by (distance, id)."""
+    import torch
+    rng = np.random.default_rng(1)
+    n, dim, nq, k = 3000, 100, 40, 12
+    x = np.round(rng.standard_normal((n, dim)) * 3).astype(np.float32)      # coarse grid: plenty of exact ties
+    q = np.round(rng.standard_normal((nq, dim)) * 3).astype(np.float32)
+    graph = np.zeros((n, 2), dtype=np.uint32)
+    index = make_index(x, graph, 0, metric)
+    dq = torch.from_numpy(q).cuda()
+    ids = torch.empty((nq, k), dtype=torch.int64, device="cuda")
+    dists = torch.empty((nq, k), dtype=torch.float32, device="cuda")
+    index.exhaustive_device(dq.data_ptr(), np.float32, nq, k, ids.data_ptr(), dists.data_ptr(),
+                            stream=torch.cuda.current_stream().cuda_stream or 1)
+    torch.cuda.synchronize()
+    ids, dists = ids.cpu().numpy(), dists.cpu().numpy()
+    for i in range(nq):
+        d = oracle.distance_rows(metric, q[i], x)
+        key = -d if metric != "l2" else d
+        order = np.lexsort((np.arange(n), key))[:k]
+        assert np.array_equal(ids[i], order), (metric, i)
+        assert np.array_equal(bits(dists[i]), bits(d[order]))
