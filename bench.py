@@ -33,6 +33,15 @@ WORKLOADS = {
     # name: n, dim, dtype, metric, nq, k, window, max_degree, build window
     "c2-1Mx96-f32-L2-w128": dict(n=1_000_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
                                  max_degree=64, build_window=128, alpha=1.2),
+    # reduced-size stand-ins for BASELINE configs[2..4] (the full sizes need a GPU graph builder: the reference's
+    # CPU builder takes ~36 s per million 96-d vectors on the box's 16-core quota)
+    "c3s-200kx768-f16-IP-w128": dict(n=200_000, dim=768, dtype="float16", metric="ip", nq=10_000, k=10, window=128,
+                                     max_degree=64, build_window=128, alpha=0.95),
+    "c4s-1Mx96-lvq8-L2-w128": dict(n=1_000_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
+                                   max_degree=64, build_window=128, alpha=1.2, storage="lvq8",
+                                   graph_from="c2-1Mx96-f32-L2-w128"),
+    "c5s-2Mx96-f16-L2-sharded": dict(n=2_000_000, dim=96, dtype="float16", metric="l2", nq=10_000, k=10, window=128,
+                                     max_degree=64, build_window=128, alpha=1.2, sharded=True),
     "tiny-100kx96-f32-L2-w128": dict(n=100_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
                                      max_degree=64, build_window=128, alpha=1.2),
 }
@@ -64,31 +73,41 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 # workload: data + graph (cached per box under /tmp, rank 0 builds)
 # ------------------------------------------------------------------------------------------------
-def load_workload(name, rank, world, barrier):
-    from scalablevectorsearch_b200.synthetic import clustered_unit_vectors
-    w = WORKLOADS[name]
-    t0 = time.time()
-    base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
-    key = hashlib.sha1(json.dumps(w, sort_keys=True).encode()).hexdigest()[:12]
-    cache = os.path.join(os.environ.get("SVSB200_CACHE", "/tmp/svsb200_cache"), f"graph_{name}_{key}.npy")
-    if rank == 0 and not os.path.exists(cache):
+def build_graph_cached(tag, w, base, rank_builds, barrier):
+    """Vamana graph from the reference's own CPU builder (oracle/_ref), cached per box under /tmp."""
+    key = hashlib.sha1(json.dumps({k: w[k] for k in ("n", "dim", "dtype", "metric", "max_degree", "build_window",
+                                                       "alpha")}, sort_keys=True).encode()).hexdigest()[:12]
+    cache = os.path.join(os.environ.get("SVSB200_CACHE", "/tmp/svsb200_cache"), f"graph_{tag}_{key}.npy")
+    if rank_builds and not os.path.exists(cache):
         from oracle.bindings import RefLib   # checker/baseline infrastructure: builds the graph only
         if not RefLib.available():
             raise SystemExit("oracle/_ref/libsvsref.so is missing: run `python -c 'import __graft_entry__ as g; "
                              "g.build()'` where /root/reference exists (the graph comes from the reference builder)")
         os.makedirs(os.path.dirname(cache), exist_ok=True)
         t1 = time.time()
+        threads = max(1, effective_cpus() // w.get("build_share", 1))
         graph, ep = RefLib().build(base, w["metric"], w["max_degree"], w["build_window"], alpha=w["alpha"],
-                                   threads=effective_cpus())
-        log(f"reference auto_build n={w['n']} R={w['max_degree']} on {effective_cpus()} threads: {time.time() - t1:.1f} s, "
-            f"avg degree {graph[:, 0].mean():.1f}")
+                                   threads=threads)
+        log(f"reference auto_build {tag} n={base.shape[0]} dim={base.shape[1]} R={w['max_degree']} on {threads} threads: "
+            f"{time.time() - t1:.1f} s, avg degree {graph[:, 0].mean():.1f}")
         tmp = cache + f".tmp{os.getpid()}"
         with open(tmp, "wb") as f:
             np.save(f, np.concatenate([np.array([[ep] + [0] * w["max_degree"]], dtype=np.uint32), graph]))
         os.replace(tmp, cache)
     barrier()
     blob = np.load(cache, mmap_mode="r")
-    ep, graph = int(blob[0, 0]), np.ascontiguousarray(blob[1:])
+    return int(blob[0, 0]), np.ascontiguousarray(blob[1:])
+
+
+def load_workload(name, rank, world, barrier):
+    from scalablevectorsearch_b200.synthetic import clustered_unit_vectors
+    w = WORKLOADS[name]
+    t0 = time.time()
+    base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
+    if w["dtype"] == "float16":
+        base = base.astype(np.float16)
+    gname = w.get("graph_from", name)
+    ep, graph = build_graph_cached(gname, WORKLOADS[gname], base, rank == 0, barrier)
     log(f"rank {rank}: workload {name} ready in {time.time() - t0:.1f} s (entry point {ep})")
     return w, base, queries, graph, ep
 
@@ -173,7 +192,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, w, graph),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
                          "sample": f"full {w['nq']}-query batch x {len(times)} steps, {threads} threads = container CPU quota "
@@ -216,7 +235,16 @@ def run_ours(args):
         w = dict(w, nq=args.batch)
         queries = queries[:args.batch]
     metric = {"l2": DistanceType.L2, "ip": DistanceType.MIP, "cosine": DistanceType.Cosine}[w["metric"]]
-    index = Vamana.from_arrays(base, graph, ep, metric, device=local_rank)
+    row_bytes = w["dim"] * base.dtype.itemsize
+    lvq = None
+    if w.get("storage") == "lvq8":
+        from scalablevectorsearch_b200 import lvq8_compress
+        rows, mean = lvq8_compress(base, device=local_rank)
+        lvq = (rows, mean)
+        row_bytes = rows.shape[1]
+        index = Vamana.from_arrays(rows, graph, ep, metric, device=local_rank, lvq8=(w["dim"], mean))
+    else:
+        index = Vamana.from_arrays(base, graph, ep, metric, device=local_rank)
     index.search_parameters.buffer_config = SearchBufferConfig(w["window"])
     for opt in ("warps_per_cta", "ctas_per_sm", "rows_in_flight"):
         if getattr(args, opt):
@@ -242,7 +270,6 @@ def run_ours(args):
     hops, evals = index.counters(hi - lo)
     fetched = index.fetched(hi - lo)
     index.set_counting(False)
-    row_bytes = w["dim"] * base.dtype.itemsize
     qb = w["dim"] * queries.dtype.itemsize
     shard_bytes, bytes_per_query = algorithmic_bytes(hops, evals, fetched, w, row_bytes, qb)
     _, ref_bytes_per_query = algorithmic_bytes(hops, evals, evals, w, row_bytes, qb)
@@ -347,6 +374,8 @@ def run_ours(args):
         cpu = None
         if not args.no_cpu_baseline:
             try:
+                if lvq is not None:
+                    raise NotImplementedError("LVQ is closed source in the reference: no reference arm for this workload")
                 threads = effective_cpus()
                 times, ref_ids, _, ref = time_reference(w, base, queries, graph, ep, 5, 1, threads)
                 cpu_qps = nq / min(times)
@@ -357,12 +386,23 @@ def run_ours(args):
                                  f"1 warm-up + 5 timed searches on {threads} threads = the container's CPU quota "
                                  f"(os.cpu_count()={os.cpu_count()})",
                        "ids_identical_to_gpu": ids_equal}
+            except NotImplementedError:
+                from oracle.bindings import OracleLib   # own-spec LVQ-8: the CPU checker is the baseline ("port")
+                oidx = OracleLib().lvq8_index(lvq[0], w["dim"], lvq[1], graph, ep, w["metric"])
+                ns = 256
+                t0 = time.perf_counter()
+                o_ids, _ = oidx.search(queries[:ns], k, w["window"], w["window"])
+                dt = time.perf_counter() - t0
+                cpu = {"value": ns / dt, "unit": "queries/s", "cores": 1, "kind": "port",
+                       "sample": f"oracle/vamana_oracle.c LVQ-8 restatement, first {ns} queries, 1 thread (scalar)",
+                       "ids_identical_to_gpu": bool(np.array_equal(o_ids, ids_all[:ns].cpu().numpy().astype(np.uint64)))}
             except Exception as e:   # noqa: BLE001
                 cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
         line = {
             "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "dtype": "f32" if lvq is None else "f32 (fused LVQ-8 decode)", "data": "synthetic",
             "config": dict(workload_config(args.workload, w, graph), recall_at_10=round(recall, 4),
                            parallelism=f"replicas x{world}, query shards, NCCL all-gather of top-k"),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * w["dim"] * 4),
@@ -392,6 +432,79 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """Mode B (BASELINE configs[4] shape): base vectors split into one contiguous id range per GPU,
+    each shard with its own reference-built graph and entry point; every rank searches all queries, NCCL all-gather
+    of the per-shard top-k, TotalOrder merge on the GPU.  Checker: the reference on each shard + the same merge."""
+    import torch
+    import torch.distributed as dist
+    from scalablevectorsearch_b200 import DistanceType, SearchBufferConfig, Vamana
+    from scalablevectorsearch_b200.multi_gpu import (ShardedSearch, balance, cuda_local_search,
+                                                     merge_topk_reference_order)
+    from scalablevectorsearch_b200.synthetic import clustered_unit_vectors
+    rank, local_rank, world = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
+    w = WORKLOADS[args.workload]
+    base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
+    lo, hi = balance(w["n"], world, rank)
+    shard = np.ascontiguousarray(base[lo:hi].astype(np.float16 if w["dtype"] == "float16" else np.float32))
+    del base
+    ws = dict(w, n=hi - lo, build_share=world)
+    ep, graph = build_graph_cached(f"{args.workload}_shard{rank}of{world}", ws, shard, True, lambda: None)
+    barrier()
+    metric = {"l2": DistanceType.L2, "ip": DistanceType.MIP}[w["metric"]]
+    index = Vamana.from_arrays(shard, graph, ep, metric, device=local_rank)
+    index.search_parameters.buffer_config = SearchBufferConfig(w["window"])
+    nq, k = w["nq"], w["k"]
+    q_dev = torch.from_numpy(queries).to(dev)
+    searcher = ShardedSearch(cuda_local_search(index), id_offset=lo, greater=w["metric"] != "l2")
+    for _ in range(max(args.warmup, 3)):
+        ids, d = searcher.search(q_dev, k)
+    torch.cuda.synchronize()
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for _ in range(args.steps):
+        ids, d = searcher.search(q_dev, k)
+    stop.record()
+    torch.cuda.synchronize()
+    barrier()
+    t = torch.tensor([start.elapsed_time(stop)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    # checker: reference CPU search on this shard for a sample, gathered and merged on the host
+    from oracle.bindings import RefLib
+    ns = 200
+    r_ids, r_d = RefLib().index(shard, graph, ep, w["metric"], threads=max(1, effective_cpus() // world)).search(
+        queries[:ns], k, w["window"], w["window"])
+    r_ids = r_ids.astype(np.int64) + lo
+    parts = [None] * world
+    if world > 1:
+        dist.all_gather_object(parts, (r_ids, r_d))
+    else:
+        parts = [(r_ids, r_d)]
+    if rank == 0:
+        want_ids, want_d = merge_topk_reference_order(np.stack([p_[0] for p_ in parts]), np.stack([p_[1] for p_ in parts]), k,
+                                                      w["metric"] != "l2")
+        ok = bool(np.array_equal(want_ids, ids[:ns].cpu().numpy()) and np.array_equal(want_d, d[:ns].cpu().numpy()))
+        qps = nq * args.steps / (float(t[0]) * 1e-3)
+        print(json.dumps({
+            "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": args.workload, "n": w["n"], "shards": world, "dim": w["dim"], "base_dtype": w["dtype"],
+                       "distance": w["metric"], "batch": nq, "k": k, "search_window": w["window"],
+                       "parallelism": f"index sharded x{world} (own graph per shard), NCCL all-gather + TotalOrder merge"},
+            "matches_reference_per_shard_plus_merge": ok, "checked_queries": ns}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -410,7 +523,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weak", action="store_true", help="(reserved) per-GPU batch fixed as N grows")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if WORKLOADS[args.workload].get("sharded"):
+        run_sharded(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)
