@@ -42,6 +42,7 @@ struct SearchParams {
     int greater;               // comparator std::greater (IP / cosine): keys are negated
     int sq;                    // rows are scalar-quantised codes
     int lvq;                   // rows are LVQ-8 (mean-removed, per-vector delta/lower)
+    int no_split;              // tuning: keep wide rows on the narrow (G threads per row) mapping
     float scale, bias, scale_sq;
     // prepared queries (output of prepare_queries)
     const float* qf;           // [nq][qstride] fp32 operands of the float tree

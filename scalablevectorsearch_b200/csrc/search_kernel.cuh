@@ -269,6 +269,123 @@ __device__ __forceinline__ void float_rows(
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Wide rows (dim >= 256).  The four accumulators s0..s3 of the main loop are independent fma
+// chains until the single combine (s0+s1)+(s2+s3), so a row is spread over 4 x G threads:
+// thread (kk, tl) owns accumulator kk of lanes [LPT*tl, LPT*tl+LPT) and reads only the
+// chunks 4b+kk.  Four times more threads per row = four times shorter dependent chains and
+// finer-grained passes when only a handful of (large) rows pass the visited filter.
+// Same expression tree, same bits.
+// ---------------------------------------------------------------------------------------
+template <int ROWT, int OP, int NROWS>
+__device__ __forceinline__ void float_rows_split(
+    const SearchParams& p, const float* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
+    float (&sum)[NROWS], float (&nrm)[NROWS]) {
+    using R = Row<ROWT>;
+    constexpr int LPT = R::LPT;
+    constexpr int G = 16 / LPT;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const int tl = t % G, kk = t / G;
+    const int D = int(p.dim);
+    const bool sqcos = (OP == OP_COSF) && p.sq;
+    float lvq_delta[NROWS], lvq_lower[NROWS];
+    if constexpr (ROWT == ROW_LVQ8) {
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+            lvq_delta[r] = 0.f;
+            lvq_lower[r] = 0.f;
+            if (rowp[r]) {
+                const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rowp[r] + p.lvq_const_offset));
+                const __half2 h = *reinterpret_cast<const __half2*>(&c);
+                lvq_delta[r] = __low2float(h);
+                lvq_lower[r] = __high2float(h);
+            }
+        }
+    }
+    auto element = [&](int r, float y) -> float {
+        if constexpr (ROWT == ROW_LVQ8) {
+            return __fmaf_rn(lvq_delta[r], y, lvq_lower[r]);
+        } else {
+            return sqcos ? __fadd_rn(__fmul_rn(p.scale, y), p.bias) : y;
+        }
+    };
+    float s[NROWS][LPT], n[NROWS][LPT];
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+        for (int l = 0; l < LPT; ++l) {
+            s[r][l] = 0.0f;
+            n[r][l] = 0.0f;
+        }
+    const int thread_elem = LPT * tl;
+    const int nblk = D >> 6;
+    auto step = [&](const typename R::raw_t (&raw)[NROWS], int e0, int limit) {
+        float x[LPT];
+#pragma unroll
+        for (int l = 0; l < LPT; l += 4) {
+            float4 qv = *reinterpret_cast<const float4*>(q_s + e0 + l);
+            x[l] = qv.x; x[l + 1] = qv.y; x[l + 2] = qv.z; x[l + 3] = qv.w;
+        }
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r) {
+            if (!rowp[r]) continue;
+            float y[LPT];
+            R::cvt(raw[r], y);
+#pragma unroll
+            for (int l = 0; l < LPT; ++l)
+                if (e0 + l < limit) accumulate<OP>(s[r][l], n[r][l], x[l], element(r, y[l]));
+        }
+    };
+    // main loop: this thread's accumulator sees chunks kk, kk+4, kk+8, ... in order;
+    // four blocks of loads are put in flight before they are consumed.
+    int b = 0;
+    for (; b + 4 <= nblk; b += 4) {
+        typename R::raw_t raw[4][NROWS];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int r = 0; r < NROWS; ++r)
+                if (rowp[r]) raw[u][r] = R::load(rowp[r] + size_t((b + u) * 64 + 16 * kk + thread_elem) * R::ESIZE);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) step(raw[u], (b + u) * 64 + 16 * kk + thread_elem, D);
+    }
+    for (; b < nblk; ++b) {
+        typename R::raw_t raw[NROWS];
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+            if (rowp[r]) raw[r] = R::load(rowp[r] + size_t(b * 64 + 16 * kk + thread_elem) * R::ESIZE);
+        step(raw, b * 64 + 16 * kk + thread_elem, D);
+    }
+    if (nblk > 0) {
+        // s0 = (s0 + s1) + (s2 + s3): partners kk^1 then kk^2 (fp add is commutative)
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+#pragma unroll
+            for (int l = 0; l < LPT; ++l) {
+                float v = __fadd_rn(s[r][l], __shfl_xor_sync(FULL, s[r][l], G));
+                s[r][l] = __fadd_rn(v, __shfl_xor_sync(FULL, v, 2 * G));
+                if constexpr (OP == OP_COSF) {
+                    float w = __fadd_rn(n[r][l], __shfl_xor_sync(FULL, n[r][l], G));
+                    n[r][l] = __fadd_rn(w, __shfl_xor_sync(FULL, w, 2 * G));
+                }
+            }
+    }
+    // tail chunks go into s0 in order; every kk replica computes the same values
+    for (int e = nblk * 64; e < D; e += 16) {
+        typename R::raw_t raw[NROWS];
+        const int e0 = e + thread_elem;
+#pragma unroll
+        for (int r = 0; r < NROWS; ++r)
+            if (rowp[r] && e0 < D) raw[r] = R::load(rowp[r] + size_t(e0) * R::ESIZE);
+        if (e0 < D) step(raw, e0, D);
+    }
+#pragma unroll
+    for (int r = 0; r < NROWS; ++r) {
+        sum[r] = reduce_lanes<LPT>(s[r]);
+        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(n[r]);
+    }
+}
+
 // Exact integer sums for (int8,int8)/(uint8,uint8): groups of 4 threads, 16-byte loads,
 // dp4a.  Order-free (integer), so any lane split is bit-exact.
 template <int ROWT, int NROWS>
@@ -340,12 +457,12 @@ __device__ __forceinline__ float finish_distance(const SearchParams& p, float su
 // One pass of the neighbour expansion: NR rows per thread group, GROUPS groups per warp.
 // Candidate `base + r*GROUPS + g` is evaluated by group g in slot r; thread 0 of the group
 // publishes the sort key into ckey[].
-template <int ROWT, int OP, int DS, int NR>
+template <int ROWT, int OP, int DS, int NR, int KS = 1>
 __device__ __forceinline__ void eval_pass(const SearchParams& p, const float* q_s, const char* vectors,
                                           const uint32_t* cid, float* ckey, uint32_t base, uint32_t count, int g, int t,
                                           float aux0, float aux1, float ksign) {
     constexpr bool kInt = (OP >= OP_L2I);
-    constexpr int G = kInt ? 4 : 16 / Row<ROWT>::LPT;
+    constexpr int G = kInt ? 4 : KS * 16 / Row<ROWT>::LPT;
     constexpr int GROUPS = 32 / G;
     const char* rowp[NR];
     uint32_t idx[NR];
@@ -358,6 +475,8 @@ __device__ __forceinline__ void eval_pass(const SearchParams& p, const float* q_
     int ixy[NR], iyy[NR];
     if constexpr (kInt) {
         int_rows<ROWT, NR>(p, reinterpret_cast<const uint8_t*>(q_s), rowp, t, ixy, iyy);
+    } else if constexpr (KS == 4) {
+        float_rows_split<ROWT, OP, NR>(p, q_s, rowp, t, sum, nrm);
     } else {
         float_rows<ROWT, OP, DS, NR>(p, q_s, rowp, t, sum, nrm);
     }
@@ -394,10 +513,10 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // index/flat/flat.h:159,421-465, used here for ground truth): the "neighbours" of every step
 // are the next block of consecutive ids, there is no visited filter and no expansion order;
 // the sorted buffer (window = capacity = k) ends up holding the exact top-k, ties by id.
-template <int ROWT, int OP, int DS, int NROWS, bool EXH = false>
+template <int ROWT, int OP, int DS, int NROWS, bool EXH = false, int KS = 1>
 __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(const __grid_constant__ SearchParams p) {
     constexpr bool kInt = (OP >= OP_L2I);
-    constexpr int G = kInt ? 4 : 16 / Row<ROWT>::LPT;     // threads per row
+    constexpr int G = kInt ? 4 : KS * 16 / Row<ROWT>::LPT;     // threads per row
     constexpr int GROUPS = 32 / G;                        // rows per warp per slot
     constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -453,7 +572,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
         if constexpr (!EXH) {
             if (lane == 0) cid[0] = p.entry_point;
             __syncwarp();
-            eval_pass<ROWT, OP, DS, 1>(p, q_s, vectors, cid, ckey, 0, 1, g, t, aux0, aux1, ksign);
+            eval_pass<ROWT, OP, DS, 1, KS>(p, q_s, vectors, cid, ckey, 0, 1, g, t, aux0, aux1, ksign);
             __syncwarp();
             if (lane == 0) {
                 bkey[0] = ckey[0];
@@ -559,10 +678,10 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
             // takes the single-row pass (half the instructions).
             for (uint32_t base = 0; base < deg;) {
                 if (SVSB200_ADAPTIVE && NROWS > 1 && deg - base <= GROUPS) {
-                    eval_pass<ROWT, OP, DS, 1>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
+                    eval_pass<ROWT, OP, DS, 1, KS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
                     base += GROUPS;
                 } else {
-                    eval_pass<ROWT, OP, DS, NROWS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
+                    eval_pass<ROWT, OP, DS, NROWS, KS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
                     base += NROWS * GROUPS;
                 }
             }
@@ -677,9 +796,9 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
 }
 
 // Host-side launch helper shared by the per-type translation units.
-template <int ROWT, int OP, int DS, int NROWS>
+template <int ROWT, int OP, int DS, int NROWS, int KS = 1>
 cudaError_t launch_one(const SearchParams& p, const LaunchConfig& cfg) {
-    auto kernel = vamana_search_kernel<ROWT, OP, DS, NROWS>;
+    auto kernel = vamana_search_kernel<ROWT, OP, DS, NROWS, false, KS>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
     if (err != cudaSuccess) return err;
     int grid = cfg.grid;
@@ -719,6 +838,8 @@ template <int ROWT, int OP> cudaError_t launch_dims(const SearchParams& p, const
     if constexpr (OP < OP_L2I) {
         if (p.dim == 96) return nrows == 1 ? launch_one<ROWT, OP, 96, 1>(p, cfg) : launch_one<ROWT, OP, 96, 2>(p, cfg);
         if (p.dim == 128) return nrows == 1 ? launch_one<ROWT, OP, 128, 1>(p, cfg) : launch_one<ROWT, OP, 128, 2>(p, cfg);
+        // wide rows: accumulators split over 4x the threads (float_rows_split)
+        if (p.dim >= 256 && !p.no_split) return launch_one<ROWT, OP, 0, 2, 4>(p, cfg);
     }
     return nrows == 1 ? launch_one<ROWT, OP, 0, 1>(p, cfg) : launch_one<ROWT, OP, 0, 2>(p, cfg);
 }

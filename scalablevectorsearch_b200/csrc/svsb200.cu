@@ -79,7 +79,7 @@ struct svsb200_index {
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
     bool timed = false;
     // options
-    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1;
+    long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
     std::mutex mutex;
 };
 
@@ -537,6 +537,8 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
     } else if (key == "rows_in_flight") {
         if (value < 0 || value > 2) return fail("rows_in_flight must be in [0, 2]");
         ix->rows_in_flight = value;
+    } else if (key == "no_split") {
+        ix->no_split = value;
     } else if (key == "filter_tag16") {
         ix->filter_tag16 = value;
     } else if (key == "visited_filter_slots") {
@@ -633,6 +635,7 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
     p.lvq = ix->storage == SVSB200_LVQ8;
+    p.no_split = int(ix->no_split);
     p.lvq_const_offset = ix->lvq_const_offset;
     p.scale = ix->scale;
     p.bias = ix->bias;

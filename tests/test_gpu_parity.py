@@ -94,7 +94,7 @@ def test_visited_filter_never_changes_results(dataset, ref_outputs, slots):
         assert fetched.sum() < evals.sum()
 
 
-@pytest.mark.parametrize("dim,max_degree", [(17, 8), (96, 64), (100, 32), (223, 24), (768, 16)])
+@pytest.mark.parametrize("dim,max_degree", [(17, 8), (96, 64), (100, 32), (223, 24), (300, 12), (768, 16)])
 @pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
 def test_ragged_dims_vs_oracle(oracle, dim, max_degree, metric):
     """Non-integer data, ragged dimensions (masked tail), several graph degrees, every float pair."""
