@@ -537,7 +537,6 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
     uint32_t* sid = spos + p.deg_pad;
     uint32_t* sfp = sid + p.deg_pad;
     uint32_t* filt = sfp + p.deg_pad;                                   // [filter_slots] visited ids (or 16-bit tags)
-    uint16_t* filt16 = reinterpret_cast<uint16_t*>(filt);
     uint32_t* adj = filt + (p.filter_tag16 ? p.filter_slots / 2 : p.filter_slots);   // [2][deg_pad] staged adjacency rows
 
     const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
@@ -639,7 +638,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
                 // graph.get_node(node): adjacency row, neighbours first, kNoNeighbor padding.
                 // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
                 const uint32_t* grow = p.graph + size_t(node) * p.gstride;
-                const uint32_t fmask = p.filter_slots - 1;
+                const uint32_t fmask = (p.filter_tag16 ? p.filter_slots / 2 : p.filter_slots) - 1;   // sets
                 uint32_t ncand = 0;
                 for (uint32_t j0 = 0; j0 < p.gstride; j0 += 32) {
                     uint32_t j = j0 + lane;
@@ -650,10 +649,14 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
                         // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember
                         const uint32_t slot = nb & fmask;
                         if (p.filter_tag16) {
-                            // slot index + 16-bit tag reconstruct the full id: still exact
-                            const uint16_t tag = uint16_t(nb >> p.filter_shift);
-                            fresh = filt16[slot] != tag;
-                            if (fresh) filt16[slot] = tag;
+                            // Two-way set-associative, LRU by position: a set is one 32-bit word
+                            // holding two 16-bit tags (set index + tag reconstruct the full id,
+                            // so a hit is exact).  A miss pushes the new tag to the front and
+                            // drops the older of the two.
+                            const uint32_t tag = nb >> p.filter_shift;
+                            const uint32_t set = filt[slot];
+                            fresh = ((set & 0xFFFFu) != tag) && ((set >> 16) != tag);
+                            if (fresh) filt[slot] = (set << 16) | tag;
                         } else {
                             fresh = filt[slot] != nb;
                             if (fresh) filt[slot] = nb;

@@ -658,10 +658,15 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.evals = ix->counting ? ix->evals.ptr : nullptr;
     p.fetched = ix->counting ? ix->fetched.ptr : nullptr;
     p.filter_slots = exhaustive ? 0u : (ix->filter_slots < 0 ? 4096u : uint32_t(ix->filter_slots));
+    // 16-bit tags (two per 32-bit set, 2-way LRU) are exact as long as every id >> log2(sets) fits below
+    // the 0xFFFF "empty" mark; larger indexes fall back to direct-mapped 32-bit entries.
     p.filter_shift = 0;
-    while ((1u << p.filter_shift) < p.filter_slots) ++p.filter_shift;
-    // 16-bit tags are exact as long as every id >> shift fits below the 0xFFFF "empty" mark
-    p.filter_tag16 = p.filter_slots && ((uint64_t(ix->n - 1) >> p.filter_shift) < 0xFFFFull) && ix->filter_tag16 != 0;
+    while ((2u << p.filter_shift) < p.filter_slots) ++p.filter_shift;   // log2(sets) with sets = slots / 2
+    p.filter_tag16 = p.filter_slots >= 2 && ((uint64_t(ix->n - 1) >> p.filter_shift) < 0xFFFFull) && ix->filter_tag16 != 0;
+    if (!p.filter_tag16) {
+        p.filter_shift = 0;
+        while ((1u << p.filter_shift) < p.filter_slots) ++p.filter_shift;
+    }
 
     LaunchConfig cfg{};
     const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
