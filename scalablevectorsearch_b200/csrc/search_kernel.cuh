@@ -110,6 +110,36 @@ template <int OP> __device__ __forceinline__ void accumulate(float& s, float& nr
     }
 }
 
+// Blackwell packs two IEEE fp32 operations into one instruction (PTX add/sub/fma.rn.f32x2 ->
+// SASS FADD2 / FFMA2): each half rounds exactly like the scalar _rn form, so the expression
+// tree -- and every bit of the result -- is unchanged while the FP instruction count halves.
+__device__ __forceinline__ float2 fsub2_rn(float2 a, float2 b) {
+    unsigned long long d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2_rn(float2 a, float2 b) {
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 ffma2_rn(float2 a, float2 b, float2 c) {
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+template <int OP> __device__ __forceinline__ void accumulate2(float2& s, float2& nrm, float2 x, float2 y) {
+    if constexpr (OP == OP_L2F) {
+        float2 c = fsub2_rn(x, y);
+        s = ffma2_rn(c, c, s);
+    } else {
+        s = ffma2_rn(x, y, s);
+        if constexpr (OP == OP_COSF) {
+            nrm = ffma2_rn(y, y, nrm);
+        }
+    }
+}
+
 // _mm512_reduce_add_ps over the 16 logical lanes spread across the G threads of a group.
 template <int LPT> __device__ __forceinline__ float reduce_lanes(float (&s)[LPT]) {
     constexpr unsigned FULL = 0xFFFFFFFFu;
@@ -171,16 +201,17 @@ __device__ __forceinline__ void float_rows(
         }
     };
 
-    float s[NROWS][4][LPT];
-    float n[NROWS][4][LPT];
+    constexpr int HP = LPT / 2;   // lane pairs: packed f32x2 arithmetic
+    float2 s[NROWS][4][HP];
+    float2 n[NROWS][4][HP];
 #pragma unroll
     for (int r = 0; r < NROWS; ++r)
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                s[r][k][l] = 0.0f;
-                n[r][k][l] = 0.0f;
+            for (int l = 0; l < HP; ++l) {
+                s[r][k][l] = make_float2(0.0f, 0.0f);
+                n[r][k][l] = make_float2(0.0f, 0.0f);
             }
 
     const int thread_elem = LPT * t;                 // first element of this thread in a chunk
@@ -208,9 +239,9 @@ __device__ __forceinline__ void float_rows(
                 float y[LPT];
                 R::cvt(raw[r][k], y);
 #pragma unroll
-                for (int l = 0; l < LPT; ++l) {
-                    float yy = element(r, y[l]);
-                    accumulate<OP>(s[r][k][l], n[r][k][l], x[l], yy);
+                for (int l = 0; l < HP; ++l) {
+                    accumulate2<OP>(s[r][k][l], n[r][k][l], make_float2(x[2 * l], x[2 * l + 1]),
+                                    make_float2(element(r, y[2 * l]), element(r, y[2 * l + 1])));
                 }
             }
         }
@@ -220,10 +251,10 @@ __device__ __forceinline__ void float_rows(
 #pragma unroll
         for (int r = 0; r < NROWS; ++r)
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                s[r][0][l] = __fadd_rn(__fadd_rn(s[r][0][l], s[r][1][l]), __fadd_rn(s[r][2][l], s[r][3][l]));
+            for (int l = 0; l < HP; ++l) {
+                s[r][0][l] = fadd2_rn(fadd2_rn(s[r][0][l], s[r][1][l]), fadd2_rn(s[r][2][l], s[r][3][l]));
                 if constexpr (OP == OP_COSF)
-                    n[r][0][l] = __fadd_rn(__fadd_rn(n[r][0][l], n[r][1][l]), __fadd_rn(n[r][2][l], n[r][3][l]));
+                    n[r][0][l] = fadd2_rn(fadd2_rn(n[r][0][l], n[r][1][l]), fadd2_rn(n[r][2][l], n[r][3][l]));
             }
     }
     // Up to three full 16-wide chunks plus one masked remainder, all into s0, in order
@@ -252,10 +283,12 @@ __device__ __forceinline__ void float_rows(
                     float y[LPT];
                     R::cvt(raw[r][k], y);
 #pragma unroll
-                    for (int l = 0; l < LPT; ++l) {
-                        if (e0 + l < D) {
-                            float yy = element(r, y[l]);
-                            accumulate<OP>(s[r][0][l], n[r][0][l], x[l], yy);
+                    for (int l = 0; l < HP; ++l) {
+                        if (e0 + 2 * l + 1 < D) {
+                            accumulate2<OP>(s[r][0][l], n[r][0][l], make_float2(x[2 * l], x[2 * l + 1]),
+                                            make_float2(element(r, y[2 * l]), element(r, y[2 * l + 1])));
+                        } else if (e0 + 2 * l < D) {   // odd dimension: only the low half is a live lane
+                            accumulate<OP>(s[r][0][l].x, n[r][0][l].x, x[2 * l], element(r, y[2 * l]));
                         }
                     }
                 }
@@ -264,8 +297,16 @@ __device__ __forceinline__ void float_rows(
     }
 #pragma unroll
     for (int r = 0; r < NROWS; ++r) {
-        sum[r] = reduce_lanes<LPT>(s[r][0]);
-        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(n[r][0]);
+        float sl[LPT], nl[LPT];
+#pragma unroll
+        for (int l = 0; l < HP; ++l) {
+            sl[2 * l] = s[r][0][l].x;
+            sl[2 * l + 1] = s[r][0][l].y;
+            nl[2 * l] = n[r][0][l].x;
+            nl[2 * l + 1] = n[r][0][l].y;
+        }
+        sum[r] = reduce_lanes<LPT>(sl);
+        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(nl);
     }
 }
 
