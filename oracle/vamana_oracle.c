@@ -397,9 +397,11 @@ static int emplace_visited(Buffer* b, uint32_t id) { /* :462-464 + filter.h:111-
     *v = (uint16_t)(id >> 16);
     return hit;
 }
-static void buffer_insert(Buffer* b, Entry n) { /* :353-403 */
+/* Returns what the reference's insert returns: the insertion index, size() when the
+ * candidate is skipped, size()+1 when it is a duplicate id. */
+static size_t buffer_insert(Buffer* b, Entry n) { /* :353-403 */
     int full = b->size == b->capacity;
-    if (full && (b->capacity == 0 || cmp(b, b->e[b->size - 1].dist, n.dist))) return; /* can_skip */
+    if (full && (b->capacity == 0 || cmp(b, b->e[b->size - 1].dist, n.dist))) return b->size; /* can_skip */
     /* lower_bound with !cmp(d, other): first slot whose entry is strictly worse than d. */
     size_t lo = 0, hi = b->size;
     while (lo < hi) {
@@ -413,18 +415,14 @@ static void buffer_insert(Buffer* b, Entry n) { /* :353-403 */
     for (size_t back = pos; back > 0;) { /* duplicate-id scan over the equal-distance run */
         --back;
         if (cmp(b, b->e[back].dist, n.dist)) break;
-        if (b->e[back].id == n.id) return;
+        if (b->e[back].id == n.id) return b->size + 1;
     }
     memmove(&b->e[pos + 1], &b->e[pos], (b->size - pos) * sizeof(Entry)); /* copy_backward */
     b->e[pos] = n;
     b->size = b->size + 1 < b->capacity ? b->size + 1 : b->capacity;
     if (pos < b->best_unvisited) b->best_unvisited = pos;
+    return pos;
 }
-static int entry_cmp_less(const void* x, const void* y) {
-    float a = ((const Entry*)x)->dist, c = ((const Entry*)y)->dist;
-    return a < c ? -1 : a > c;
-}
-
 /* ------------------------------------------------------------------------------------
  * Index + greedy search.
  * ---------------------------------------------------------------------------------- */
@@ -452,7 +450,6 @@ static void greedy_search(const Index* ix, FixedQuery* f, const void* query, Buf
         buffer_push_back(buf, e);
         if (evals) ++*evals;
         /* buffer.sort(): a single entry point, nothing to order (:89). */
-        (void)entry_cmp_less;
     }
     while (!buffer_done(buf)) { /* :153 */
         Entry node = buffer_next(buf);
@@ -648,6 +645,59 @@ static int run_batch(Index* ix, int qtype, const void* queries, size_t nq, size_
     free(buf.e);
     free(buf.visited);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------
+ * Test-only access to the SearchBuffer restatement, so tests/ can replay the reference's own
+ * known-answer insert sequence (tests/svs/index/vamana/search_buffer.cpp:382-519) and fuzz it
+ * against an independent model (same file, :74-244).
+ * ---------------------------------------------------------------------------------- */
+void* oracle_buffer_new(size_t window, size_t capacity, int greater) {
+    Buffer* b = (Buffer*)calloc(1, sizeof(Buffer));
+    if (!b) return NULL;
+    b->window = window;
+    b->capacity = capacity;
+    b->greater = greater;
+    b->e = (Entry*)calloc(capacity + 1, sizeof(Entry));
+    return b;
+}
+void oracle_buffer_free(void* h) {
+    Buffer* b = (Buffer*)h;
+    if (!b) return;
+    free(b->e);
+    free(b);
+}
+void oracle_buffer_clear(void* h) { buffer_clear((Buffer*)h); }
+void oracle_buffer_push_back(void* h, uint32_t id, float dist) {
+    Entry e = {id, dist, 0};
+    buffer_push_back((Buffer*)h, e);
+}
+size_t oracle_buffer_insert(void* h, uint32_t id, float dist) {
+    Entry e = {id, dist, 0};
+    return buffer_insert((Buffer*)h, e);
+}
+size_t oracle_buffer_size(void* h) { return ((Buffer*)h)->size; }
+size_t oracle_buffer_best_unvisited(void* h) { return ((Buffer*)h)->best_unvisited; }
+int oracle_buffer_done(void* h) { return buffer_done((Buffer*)h); }
+uint32_t oracle_buffer_next(void* h) { return buffer_next((Buffer*)h).id; }
+void oracle_buffer_set_visited(void* h, size_t i) { ((Buffer*)h)->e[i].visited = 1; }
+void oracle_buffer_get(void* h, size_t i, uint32_t* id, float* dist, int* visited) {
+    Entry e = ((Buffer*)h)->e[i];
+    *id = e.id;
+    *dist = e.dist;
+    *visited = e.visited;
+}
+void oracle_buffer_sort(void* h) { /* buffer.sort(): std::sort by the comparator (:408) */
+    Buffer* b = (Buffer*)h;
+    for (size_t i = 1; i < b->size; ++i) {   /* insertion sort: small, and stable is fine */
+        Entry x = b->e[i];
+        size_t j = i;
+        while (j > 0 && cmp(b, x.dist, b->e[j - 1].dist)) {
+            b->e[j] = b->e[j - 1];
+            --j;
+        }
+        b->e[j] = x;
+    }
 }
 
 int oracle_index_search(void* h, int qtype, const void* queries, size_t nq, size_t k, size_t window,

@@ -541,12 +541,6 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ---------------------------------------------------------------------------------------
 // The kernel.
 // ---------------------------------------------------------------------------------------
-#ifndef SVSB200_ADAPTIVE
-#define SVSB200_ADAPTIVE 0   // measured: the extra single-row pass costs more (code size, spills) than it saves
-#endif
-#ifndef SVSB200_STAGE_ADJ
-#define SVSB200_STAGE_ADJ 1
-#endif
 #ifndef SVSB200_MIN_BLOCKS
 #define SVSB200_MIN_BLOCKS 2   // <= 128 registers: four 4-warp CTAs (16 warps) per SM
 #endif
@@ -664,7 +658,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
                 // Stage the predicted next node's adjacency row (asynchronous global->shared copy,
                 // in flight during this hop's distance evaluations and merge).
                 staged_node = kNoNeighbor;
-                if (SVSB200_STAGE_ADJ && pred_pos != 0xFFFFFFFFu) {
+                if (pred_pos != 0xFFFFFFFFu) {
                     staged_node = bid[pred_pos] & kIdMask;
                     staged_buf ^= 1u;
                     uint32_t* dst = adj + staged_buf * p.deg_pad;
@@ -717,18 +711,11 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
                 deg = ncand;   // from here on: the candidates that are actually evaluated
 
             }
-            // neighbour expansion: distance of every neighbour (greedy_search.h:190-201).
-            // A pass covers NROWS x GROUPS candidates; a remainder that fits one row per group
-            // takes the single-row pass (half the instructions).
-            for (uint32_t base = 0; base < deg;) {
-                if (SVSB200_ADAPTIVE && NROWS > 1 && deg - base <= GROUPS) {
-                    eval_pass<ROWT, OP, DS, 1, KS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
-                    base += GROUPS;
-                } else {
-                    eval_pass<ROWT, OP, DS, NROWS, KS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
-                    base += NROWS * GROUPS;
-                }
-            }
+            // neighbour expansion: distance of every neighbour (greedy_search.h:190-201),
+            // NROWS x GROUPS candidates per pass.  (A single-row pass for small remainders was
+            // measured slower: more code, more registers.)
+            for (uint32_t base = 0; base < deg; base += NROWS * GROUPS)
+                eval_pass<ROWT, OP, DS, NROWS, KS>(p, q_s, vectors, cid, ckey, base, deg, g, t, aux0, aux1, ksign);
             __syncwarp();
 
             // ---- merge the candidates into the sorted buffer (== sequential insert) ----
