@@ -186,14 +186,17 @@ def run_reference(args):
         return
     w, base, queries, graph, ep = load_workload(args.workload, 0, 1, lambda: None)
     threads = effective_cpus()
+    # the CPU path's QPS does not depend on how many GPUs our arm uses: each step is one 10k-query batch of the
+    # same workload (a bounded sample of the N x 10k global batch of the weak-scaling run)
     times, _, _, ref = time_reference(w, base, queries, graph, ep, args.steps, args.warmup, threads)
     total = sum(times)
     qps = w["nq"] * len(times) / total
     line = {
         "impl": "reference", "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.workload, w, graph),
+        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(workload_config(args.workload, w, graph), global_batch=w["nq"] * (1 if args.strong else args.gpus),
+                       batch_per_gpu=w["nq"] // (args.gpus if args.strong else 1)),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
                          "sample": f"full {w['nq']}-query batch x {len(times)} steps, {threads} threads = container CPU quota "
                                    f"(os.cpu_count()={os.cpu_count()}), "
@@ -257,7 +260,14 @@ def run_ours(args):
         name, val = kv.split("=")
         index.set_option(name, int(val))
     lib = _lib.lib()
-    nq, k = w["nq"], w["k"]
+    # Weak scaling (default, SURVEY.md 8e mode A): every GPU keeps the metric's own batch (10 000 queries), the
+    # global batch is N x that; rank r owns query block r (block 0 == the single-GPU batch).  --strong keeps the
+    # global batch at the single-GPU size and splits it, which under-fills 8 B200s (1 250 queries each).
+    weak = world > 1 and not args.strong
+    if weak:
+        from scalablevectorsearch_b200.synthetic import clustered_queries
+        queries = np.concatenate([queries] + [clustered_queries(w["nq"], w["dim"], r) for r in range(1, world)])
+    nq, k = queries.shape[0], w["k"]
     q_host = torch.from_numpy(queries).pin_memory()
     q_dev = q_host.to(dev, non_blocking=True)
     searcher = ReplicatedSearch(cuda_local_search(index))
@@ -380,12 +390,13 @@ def run_ours(args):
                 if lvq is not None:
                     raise NotImplementedError("LVQ is closed source in the reference: no reference arm for this workload")
                 threads = effective_cpus()
-                times, ref_ids, _, ref = time_reference(w, base, queries, graph, ep, 5, 1, threads)
-                cpu_qps = nq / min(times)
-                ids_equal = bool(np.array_equal(ref_ids, ids_all.cpu().numpy().astype(np.uint64)))
-                cpu = {"value": nq * len(times) / sum(times), "best": cpu_qps, "unit": "queries/s", "cores": threads,
+                nb = w["nq"]   # the metric's batch (rank 0's block)
+                times, ref_ids, _, ref = time_reference(w, base, queries[:nb], graph, ep, 5, 1, threads)
+                cpu_qps = nb / min(times)
+                ids_equal = bool(np.array_equal(ref_ids, ids_all[:nb].cpu().numpy().astype(np.uint64)))
+                cpu = {"value": nb * len(times) / sum(times), "best": cpu_qps, "unit": "queries/s", "cores": threads,
                        "kind": "reference",
-                       "sample": f"reference AVX-512 path (oracle/_ref, avx512={ref.avx512()}), full {nq}-query batch, "
+                       "sample": f"reference AVX-512 path (oracle/_ref, avx512={ref.avx512()}), full {nb}-query batch, "
                                  f"1 warm-up + 5 timed searches on {threads} threads = the container's CPU quota "
                                  f"(os.cpu_count()={os.cpu_count()})",
                        "ids_identical_to_gpu": ids_equal}
@@ -404,12 +415,15 @@ def run_ours(args):
         line = {
             "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak" if args.weak else "strong", "vs_baseline": None,
+            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
             "dtype": "f32" if lvq is None else "f32 (fused LVQ-8 decode)", "data": "synthetic",
-            "config": dict(workload_config(args.workload, w, graph), recall_at_10=round(recall, 4),
+            "config": dict(workload_config(args.workload, w, graph), recall_at_10=round(recall, 4), global_batch=nq,
+                           batch_per_gpu=hi - lo,
                            parallelism=f"replicas x{world}, query shards, NCCL all-gather of top-k"),
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * w["dim"] * 4),
-                    "d2h_bytes_per_step": int(nq * k * 12), "matches_device_path": same},
+                    "d2h_bytes_per_step": int(nq * k * 12), "matches_device_path": same,
+                    "path": "svsb200_search (C ABI) per rank on its own query block: pinned host queries in, host ids + "
+                            "distances out; max over ranks"},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -526,7 +540,9 @@ def main():
     ap.add_argument("--filter-slots", dest="filter_slots", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svsb200_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--weak", action="store_true", help="(reserved) per-GPU batch fixed as N grows")
+    ap.add_argument("--strong", action="store_true",
+                    help="keep the global batch at the single-GPU size and split it over the GPUs (default: weak "
+                         "scaling, every GPU keeps the metric's 10k-query batch)")
     args = ap.parse_args()
     if WORKLOADS[args.workload].get("sharded"):
         run_sharded(args)

@@ -23,3 +23,10 @@ def clustered_unit_vectors(n: int, nq: int, dim: int, clusters: int = 1024, sigm
     """Returns (base float32 [n,dim], queries float32 [nq,dim])."""
     centres = np.random.default_rng(CENTRES_SEED).standard_normal((clusters, dim), dtype=np.float32)
     return _mixture(n, dim, centres, BASE_SEED, sigma), _mixture(nq, dim, centres, QUERY_SEED, sigma)
+
+
+def clustered_queries(nq: int, dim: int, shard: int = 0, clusters: int = 1024, sigma: float = 0.35) -> np.ndarray:
+    """Query block number ``shard`` of the same law (block 0 == the queries of :func:`clustered_unit_vectors`);
+    used to give every GPU its own batch when per-GPU work is held fixed."""
+    centres = np.random.default_rng(CENTRES_SEED).standard_normal((clusters, dim), dtype=np.float32)
+    return _mixture(nq, dim, centres, QUERY_SEED + shard, sigma)
