@@ -237,3 +237,21 @@ def test_exhaustive_scan_is_exact_topk(oracle, metric):
         order = np.lexsort((np.arange(n), key))[:k]
         assert np.array_equal(ids[i], order), (metric, i)
         assert np.array_equal(bits(dists[i]), bits(d[order]))
+
+
+def test_assemble_from_files_like_the_reference_binding(dataset, ref_outputs, tmp_path):
+    """`svs.Vamana(config_path, GraphLoader(...), VectorDataLoader(...), distance)` (bindings/python/src/vamana.cpp:340-348)
+    over on-disk files in the reference's formats, then `search_window_size` + `search`."""
+    from scalablevectorsearch_b200 import DataType, DistanceType, GraphLoader, Vamana, VectorDataLoader, io
+    io.write_svs(str(tmp_path / "data.svs"), dataset.data)
+    io.write_svs(str(tmp_path / "graph.svs"), dataset.graph)
+    (tmp_path / "config.toml").write_text(f"[object]\nentry_point = {dataset.entry_point}\n")
+    index = Vamana(str(tmp_path / "config.toml"), GraphLoader(str(tmp_path / "graph.svs")),
+                   VectorDataLoader(str(tmp_path / "data.svs"), DataType.float32), distance=DistanceType.Cosine)
+    assert (index.size, index.dimensions, index.graph_max_degree) == (10000, 128, 128)
+    index.search_window_size = 100
+    assert index.search_parameters.buffer_config.search_buffer_capacity == 100
+    ids, dists = index.search(dataset.queries[100:], 10)
+    assert ids.dtype == np.uint64 and dists.dtype == np.float32
+    assert_same((ids, dists), ref_outputs["cosine_f32_f32_w100_c100_ids"], ref_outputs["cosine_f32_f32_w100_c100_dists"],
+                "assemble-from-files cosine w100")
