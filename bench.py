@@ -386,7 +386,7 @@ def run_ours(args):
         recall = float(np.mean([len(set(got[i]) & set(gt[i])) for i in range(sample)])) / k
 
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported at N=1 only; `--impl reference` covers every N
             try:
                 if lvq is not None:
                     raise NotImplementedError("LVQ is closed source in the reference: no reference arm for this workload")
