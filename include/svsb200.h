@@ -94,7 +94,11 @@ int svsb200_search(
 
 /* Same search with every buffer already resident in HBM on the index's device and no
  * synchronisation: enqueues on `stream` and returns (bench.py's device-resident `value`,
- * multi-GPU pipelines that feed NCCL directly). */
+ * multi-GPU pipelines that feed NCCL directly).  An index owns one set of device scratch
+ * buffers (prepared queries, work counter): searches enqueued on the same index must be
+ * ordered on one stream (or separated by a synchronisation); use one index handle per
+ * concurrent stream -- the analogue of the reference's per-thread scratch space
+ * (index/vamana/index.h:455-470). */
 int svsb200_search_device(
     svsb200_index* index, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
     size_t capacity, int use_visited_set, void* d_out_ids, int id_bytes, float* d_out_dists,
