@@ -185,6 +185,8 @@ def run_reference(args):
     if rank != 0:
         return
     w, base, queries, graph, ep = load_workload(args.workload, 0, 1, lambda: None)
+    if args.window:
+        w = dict(w, window=args.window)
     threads = effective_cpus()
     # the CPU path's QPS does not depend on how many GPUs our arm uses: each step is one 10k-query batch of the
     # same workload (a bounded sample of the N x 10k global batch of the weak-scaling run)
