@@ -350,13 +350,14 @@ __device__ __forceinline__ void float_rows_split(
             return sqcos ? __fadd_rn(__fmul_rn(p.scale, y), p.bias) : y;
         }
     };
-    float s[NROWS][LPT], n[NROWS][LPT];
+    constexpr int HP = LPT / 2;   // lane pairs: packed f32x2 arithmetic (same bits, see accumulate2)
+    float2 s[NROWS][HP], n[NROWS][HP];
 #pragma unroll
     for (int r = 0; r < NROWS; ++r)
 #pragma unroll
-        for (int l = 0; l < LPT; ++l) {
-            s[r][l] = 0.0f;
-            n[r][l] = 0.0f;
+        for (int l = 0; l < HP; ++l) {
+            s[r][l] = make_float2(0.0f, 0.0f);
+            n[r][l] = make_float2(0.0f, 0.0f);
         }
     const int thread_elem = LPT * tl;
     const int nblk = D >> 6;
@@ -373,8 +374,14 @@ __device__ __forceinline__ void float_rows_split(
             float y[LPT];
             R::cvt(raw[r], y);
 #pragma unroll
-            for (int l = 0; l < LPT; ++l)
-                if (e0 + l < limit) accumulate<OP>(s[r][l], n[r][l], x[l], element(r, y[l]));
+            for (int l = 0; l < HP; ++l) {
+                if (e0 + 2 * l + 1 < limit) {
+                    accumulate2<OP>(s[r][l], n[r][l], make_float2(x[2 * l], x[2 * l + 1]),
+                                    make_float2(element(r, y[2 * l]), element(r, y[2 * l + 1])));
+                } else if (e0 + 2 * l < limit) {   // odd dimension: only the low half is a live lane
+                    accumulate<OP>(s[r][l].x, n[r][l].x, x[2 * l], element(r, y[2 * l]));
+                }
+            }
         }
     };
     // main loop: this thread's accumulator sees chunks kk, kk+4, kk+8, ... in order;
@@ -402,12 +409,15 @@ __device__ __forceinline__ void float_rows_split(
 #pragma unroll
         for (int r = 0; r < NROWS; ++r)
 #pragma unroll
-            for (int l = 0; l < LPT; ++l) {
-                float v = __fadd_rn(s[r][l], __shfl_xor_sync(FULL, s[r][l], G));
-                s[r][l] = __fadd_rn(v, __shfl_xor_sync(FULL, v, 2 * G));
+            for (int l = 0; l < HP; ++l) {
+                auto xchg = [&](float2 v, int d) {
+                    return make_float2(__shfl_xor_sync(FULL, v.x, d), __shfl_xor_sync(FULL, v.y, d));
+                };
+                float2 v = fadd2_rn(s[r][l], xchg(s[r][l], G));
+                s[r][l] = fadd2_rn(v, xchg(v, 2 * G));
                 if constexpr (OP == OP_COSF) {
-                    float w = __fadd_rn(n[r][l], __shfl_xor_sync(FULL, n[r][l], G));
-                    n[r][l] = __fadd_rn(w, __shfl_xor_sync(FULL, w, 2 * G));
+                    float2 w = fadd2_rn(n[r][l], xchg(n[r][l], G));
+                    n[r][l] = fadd2_rn(w, xchg(w, 2 * G));
                 }
             }
     }
@@ -422,8 +432,16 @@ __device__ __forceinline__ void float_rows_split(
     }
 #pragma unroll
     for (int r = 0; r < NROWS; ++r) {
-        sum[r] = reduce_lanes<LPT>(s[r]);
-        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(n[r]);
+        float sl[LPT], nl[LPT];
+#pragma unroll
+        for (int l = 0; l < HP; ++l) {
+            sl[2 * l] = s[r][l].x;
+            sl[2 * l + 1] = s[r][l].y;
+            nl[2 * l] = n[r][l].x;
+            nl[2 * l + 1] = n[r][l].y;
+        }
+        sum[r] = reduce_lanes<LPT>(sl);
+        if constexpr (OP == OP_COSF) nrm[r] = reduce_lanes<LPT>(nl);
     }
 }
 
