@@ -124,8 +124,12 @@ uint64_t svsb200_launch_count(void);
 /* Tuning knobs (performance only; results never change):
  *   "warps_per_cta", "ctas_per_sm", "rows_in_flight" (0 restores the default);
  *   "visited_filter_slots": size of the per-query exact visited filter, the GPU form of
- *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n). */
+ *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n >= 8). */
 int svsb200_set_option(svsb200_index* index, const char* name, long value);
+/* Reads a knob back; also "last_kernel": which kernel the most recent search ran on (1 = the lean
+ * one-warp-per-CTA kernel, 0 = the generic kernel that covers every other configuration), and
+ * "generic_kernel" (set to 1 to force the generic kernel; results are identical). */
+int svsb200_get_option(svsb200_index* index, const char* name, long* value);
 
 /* Mode B of SURVEY.md §8e -- merge per-shard top-k lists (after an NCCL all-gather) into a
  * global top-k with the reference's TotalOrder (distance, then id; lib/neighbor.h:143-155).

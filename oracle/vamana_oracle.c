@@ -633,12 +633,12 @@ static int run_batch(Index* ix, int qtype, const void* queries, size_t nq, size_
         if (hops) hops[q] = h;
         if (evals) evals[q] = e;
         /* extensions.h:588-590 copies buffer[j] for j < k regardless of size; slots past
-         * `size` hold stale entries from earlier queries there.  The oracle reports them as
-         * id = UINT32_MAX / dist = NaN instead. */
+         * `size` hold stale entries from earlier queries there.  The oracle reports them the way
+         * the C ABI documents (include/svsb200.h): id = all-ones, dist = +inf (L2) / -inf (IP, cosine). */
         for (size_t j = 0; ids && j < k; ++j) {
             int valid = j < buf.size;
-            ids[q * k + j] = valid ? buf.e[j].id : 0xFFFFFFFFull;
-            dists[q * k + j] = valid ? buf.e[j].dist : NAN;
+            ids[q * k + j] = valid ? buf.e[j].id : ~0ull;
+            dists[q * k + j] = valid ? buf.e[j].dist : (buf.greater ? -INFINITY : INFINITY);
         }
     }
     fixed_query_free(&f);

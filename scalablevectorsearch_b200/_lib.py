@@ -18,7 +18,7 @@ SYMBOLS = [
     "svsb200_index_create", "svsb200_index_destroy", "svsb200_index_size",
     "svsb200_index_dimensions", "svsb200_index_max_degree", "svsb200_index_device_bytes",
     "svsb200_index_device", "svsb200_search", "svsb200_search_device", "svsb200_set_counting",
-    "svsb200_get_counters", "svsb200_get_fetched", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option",
+    "svsb200_get_counters", "svsb200_get_fetched", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option", "svsb200_get_option",
     "svsb200_merge_topk_device", "svsb200_exhaustive_device", "svsb200_lvq8_row_stride", "svsb200_lvq8_compress",
 ]
 
@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
     l.svsb200_get_fetched.argtypes = [vp, sz, vp]
     l.svsb200_last_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     l.svsb200_set_option.argtypes = [vp, C.c_char_p, C.c_long]
+    l.svsb200_get_option.argtypes = [vp, C.c_char_p, C.POINTER(C.c_long)]
     l.svsb200_merge_topk_device.argtypes = [vp, vp, sz, sz, sz, i32, vp, vp, i32, vp]
     l.svsb200_lvq8_row_stride.restype, l.svsb200_lvq8_row_stride.argtypes = sz, [sz]
     l.svsb200_lvq8_compress.argtypes = [vp, sz, sz, vp, vp, i32]

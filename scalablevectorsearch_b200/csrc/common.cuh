@@ -55,8 +55,9 @@ struct SearchParams {
     uint32_t cap_pad;          // capacity+1 rounded up to 32
     uint32_t deg_pad;          // gstride rounded up to 32
     uint32_t filter_slots;     // per-query exact visited filter (power of two, 0 = off)
-    uint32_t filter_shift;     // log2(filter_slots)
-    uint32_t filter_tag16;     // 1: entries are 16-bit tags id >> filter_shift (exact while n <= slots * 65535)
+    uint32_t filter_shift;     // tag = id >> filter_shift: log2(sets) = log2(filter_slots / 2) in tag16 mode,
+                               // log2(filter_slots) (unused: full ids are stored) otherwise
+    uint32_t filter_tag16;     // 1: two 16-bit tags per 32-bit set (exact while (n-1) >> filter_shift < 0xFFFF)
     // outputs
     void* out_ids;
     int id_bytes;
@@ -66,6 +67,7 @@ struct SearchParams {
     uint32_t* hops;              // optional per-query counters
     uint32_t* evals;
     uint32_t* fetched;           // rows actually read from HBM (after the visited filter)
+    const int* cancel;           // optional device flag: non-zero stops the batch (polled per query and per hop)
 };
 
 struct LaunchConfig {
@@ -85,8 +87,20 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap
            size_t(filter_bytes) + size_t(deg_pad) * 8;
 }
 
+// Per-CTA (= per-warp = per-query) shared memory of the fast kernel, mirrored on the host.
+__host__ __device__ inline size_t fast_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad,
+                                                  uint32_t filter_bytes) {
+    // filter | query | buffer {key,id} | candidate keys | candidate ids | sorted survivors of a group
+    return size_t((filter_bytes + 15u) & ~15u) + size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8 +
+           32 * 8 + 36 * 4;
+}
+
+constexpr int kFastMaxGW = 4;   // adjacency rows up to 128 neighbours (4 x 32) are register-staged
+
 // One launcher per (row type, op); defined in search_<type>.cu.
 template <int ROWT> cudaError_t launch_search(int op, const SearchParams& p, const LaunchConfig& cfg, int rows_in_flight);
+// The lean one-warp-per-CTA form of the same search (search_fast.cuh); defined in fast_<type>.cu.
+template <int ROWT> cudaError_t launch_search_fast(int op, const SearchParams& p, const LaunchConfig& cfg);
 // Exhaustive scan with the same distance code (ground truth / flat search).
 template <int ROWT> cudaError_t launch_search_exhaustive(int op, const SearchParams& p, const LaunchConfig& cfg);
 

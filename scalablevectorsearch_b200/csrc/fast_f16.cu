@@ -1,0 +1,15 @@
+// fast_f16.cu -- lean search-kernel instantiations (search_fast.cuh) for f16 rows.
+#include "search_fast.cuh"
+
+namespace svsb200 {
+
+template <> cudaError_t launch_search_fast<SVSB200_F16>(int op, const SearchParams& p, const LaunchConfig& cfg) {
+    switch (op) {
+        case OP_L2F: return launch_fast_dims<SVSB200_F16, OP_L2F>(p, cfg);
+        case OP_IPF: return launch_fast_dims<SVSB200_F16, OP_IPF>(p, cfg);
+        case OP_COSF: return launch_fast_dims<SVSB200_F16, OP_COSF>(p, cfg);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace svsb200

@@ -80,6 +80,8 @@ struct svsb200_index {
     bool timed = false;
     // options
     long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
+    long generic_kernel = 0;   // 1: force the generic (round-1) kernel instead of the lean one
+    int last_kernel = 0;       // 1 = lean kernel, 0 = generic kernel (introspection for tests)
     std::mutex mutex;
 };
 
@@ -252,43 +254,76 @@ __global__ void prepare_queries_kernel(const void* __restrict__ queries, uint32_
 // ---------------------------------------------------------------------------------------
 // Cross-shard top-k merge with TotalOrder (lib/neighbor.h:143-155): distance, then id.
 // ---------------------------------------------------------------------------------------
+// One warp per query selects the k smallest (key, id) pairs among all nshards * k candidates by repeated
+// "smallest entry greater than the previous output" -- a full TotalOrder sort of the candidates' prefix, so
+// the result does not depend on how ties are ordered inside a shard's list (they come out of the search
+// buffer in insertion order, not id order).  Padding entries (id = all-ones) are ignored.
+__device__ __forceinline__ uint32_t total_order_key(float d, int greater) {
+    float k = greater ? -d : d;
+    k = __fadd_rn(k, 0.0f);                       // -0 == +0 under operator<
+    const uint32_t u = __float_as_uint(k);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // monotone float -> uint
+}
 __global__ void merge_topk_kernel(const uint64_t* __restrict__ ids, const float* __restrict__ dists, uint32_t nshards,
                                   uint32_t nq, uint32_t k, int greater, uint64_t* __restrict__ out_ids,
                                   float* __restrict__ out_dists) {
-    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t q = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
     if (q >= nq) return;
-    // k-way merge of sorted lists by repeated selection (k, nshards are small).
-    uint32_t head[16];
-    for (uint32_t s = 0; s < nshards; ++s) head[s] = 0;
+    constexpr unsigned FULL = 0xFFFFFFFFu;
+    const uint32_t n = nshards * k;
+    // (key, id) of the previous output; "nothing yet" sorts before everything
+    bool have_last = false;
+    uint32_t last_key = 0;
+    uint64_t last_id = 0;
     for (uint32_t j = 0; j < k; ++j) {
-        int best = -1;
-        float bd = 0.f;
-        uint64_t bi = 0;
-        for (uint32_t s = 0; s < nshards; ++s) {
-            if (head[s] >= k) continue;
-            const size_t o = (size_t(s) * nq + q) * k + head[s];
-            const float d = dists[o];
+        uint32_t best_key = 0xFFFFFFFFu;
+        uint64_t best_id = ~uint64_t(0);
+        float best_d = 0.f;
+        bool found = false;
+        for (uint32_t c = lane; c < n; c += 32) {
+            const uint32_t sh = c / k, jj = c - sh * k;
+            const size_t o = (size_t(sh) * nq + q) * k + jj;
             const uint64_t id = ids[o];
-            if (id == ~uint64_t(0)) {
-                head[s] = k;
-                continue;
-            }
-            const bool better = best < 0 || (greater ? d > bd : d < bd) || (d == bd && id < bi);
-            if (better) {
-                best = int(s);
-                bd = d;
-                bi = id;
+            if (id == ~uint64_t(0)) continue;
+            const float d = dists[o];
+            const uint32_t key = total_order_key(d, greater);
+            if (have_last && (key < last_key || (key == last_key && id <= last_id))) continue;
+            if (!found || key < best_key || (key == best_key && id < best_id)) {
+                best_key = key;
+                best_id = id;
+                best_d = d;
+                found = true;
             }
         }
-        const size_t o = size_t(q) * k + j;
-        if (best < 0) {
-            out_ids[o] = ~uint64_t(0);
-            out_dists[o] = greater ? -INFINITY : INFINITY;
-        } else {
-            out_ids[o] = bi;
-            out_dists[o] = bd;
-            ++head[best];
+        // warp argmin over (found, key, id)
+        for (int off = 16; off; off >>= 1) {
+            const uint32_t okey = __shfl_xor_sync(FULL, best_key, off);
+            const uint64_t oid = __shfl_xor_sync(FULL, best_id, off);
+            const float od = __shfl_xor_sync(FULL, best_d, off);
+            const bool ofound = __shfl_xor_sync(FULL, int(found), off) != 0;
+            if (ofound && (!found || okey < best_key || (okey == best_key && oid < best_id))) {
+                best_key = okey;
+                best_id = oid;
+                best_d = od;
+                found = true;
+            }
         }
+        if (lane == 0) {
+            const size_t o = size_t(q) * k + j;
+            out_ids[o] = found ? best_id : ~uint64_t(0);
+            out_dists[o] = found ? best_d : (greater ? -INFINITY : INFINITY);
+        }
+        if (!found) {
+            for (uint32_t r = j + 1 + lane; r < k; r += 32) {   // nothing left: pad the tail
+                out_ids[size_t(q) * k + r] = ~uint64_t(0);
+                out_dists[size_t(q) * k + r] = greater ? -INFINITY : INFINITY;
+            }
+            return;
+        }
+        have_last = true;
+        last_key = best_key;
+        last_id = best_id;
     }
 }
 
@@ -403,7 +438,8 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
     CUDA_TRY(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 10) return fail("svsb200_index_create: device is not sm_100-class (binary is sm_100a only)");
+    if (prop.major != 10 || prop.minor != 0)
+        return fail("svsb200_index_create: device is not sm_100 (this binary holds sm_100a code only)");
 
     auto* ix = new svsb200_index();
     ix->device = device;
@@ -541,14 +577,31 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
         ix->no_split = value;
     } else if (key == "filter_tag16") {
         ix->filter_tag16 = value;
+    } else if (key == "generic_kernel") {
+        ix->generic_kernel = value;
     } else if (key == "visited_filter_slots") {
         // -1 = default; 0 = off; otherwise a power of two
         if (value > 0 && (value & (value - 1))) return fail("visited_filter_slots must be a power of two");
+        // the filter words sit in front of 16-byte aligned arrays in shared memory
+        if (value > 0 && value < 8) return fail("visited_filter_slots must be 0 (off) or at least 8");
         if (value > 16384) return fail("visited_filter_slots must be <= 16384");
         ix->filter_slots = value;
     } else {
         return fail("svsb200_set_option: unknown option " + key);
     }
+    return 0;
+}
+
+int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
+    if (!ix || !name || !value) return fail("svsb200_get_option: NULL argument");
+    const std::string key(name);
+    if (key == "last_kernel") *value = ix->last_kernel;          // 1 = lean kernel, 0 = generic kernel
+    else if (key == "warps_per_cta") *value = ix->warps_per_cta;
+    else if (key == "ctas_per_sm") *value = ix->ctas_per_sm;
+    else if (key == "rows_in_flight") *value = ix->rows_in_flight;
+    else if (key == "visited_filter_slots") *value = ix->filter_slots;
+    else if (key == "generic_kernel") *value = ix->generic_kernel;
+    else return fail("svsb200_get_option: unknown option " + key);
     return 0;
 }
 
@@ -669,19 +722,34 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     }
 
     LaunchConfig cfg{};
-    const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
-    int warps = ix->warps_per_cta ? int(ix->warps_per_cta) : 4;
     const size_t smem_limit = 227 * 1024;
-    while (warps > 1 && per_warp * warps > smem_limit) warps >>= 1;
-    if (per_warp * warps > smem_limit) return fail("search buffer capacity too large for shared memory");
-    cfg.warps_per_cta = warps;
-    cfg.smem_bytes = per_warp * warps;
-    cfg.stream = stream;
-    // grid: persistent CTAs; the launcher clamps to what is resident.  ctas_per_sm == 0
-    // means "as many as fit" (computed by the launcher through the occupancy API).
-    cfg.grid = ix->sm_count * (ix->ctas_per_sm ? int(ix->ctas_per_sm) : 0);
-    if (cfg.grid == 0 || exhaustive) cfg.grid = -ix->sm_count;   // negative: launcher multiplies by occupancy
+    // The lean kernel (search_fast.cuh) covers the common shape: 16-bit-tag filter on, adjacency rows of up to
+    // 128 neighbours; anything else (and the exhaustive scan) runs on the generic kernel.
+    const uint32_t fast_cap_pad = uint32_t(round_up(capacity, 32));
+    const size_t fast_bytes = fast_smem_bytes(p.qstride, fast_cap_pad, p.deg_pad, p.filter_slots * 2u);
+    const bool use_fast = !exhaustive && !ix->generic_kernel && p.filter_slots >= 8 && p.filter_tag16 &&
+                          p.deg_pad <= 32u * kFastMaxGW && fast_bytes <= smem_limit;
+    ix->last_kernel = use_fast ? 1 : 0;
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
+    if (use_fast) {
+        p.cap_pad = fast_cap_pad;
+        cfg.warps_per_cta = 1;
+        cfg.smem_bytes = fast_bytes;
+        cfg.stream = stream;
+        cfg.grid = ix->ctas_per_sm ? ix->sm_count * int(ix->ctas_per_sm) : -ix->sm_count;
+    } else {
+        const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
+        int warps = ix->warps_per_cta ? int(ix->warps_per_cta) : 4;
+        while (warps > 1 && per_warp * warps > smem_limit) warps >>= 1;
+        if (per_warp * warps > smem_limit) return fail("search buffer capacity too large for shared memory");
+        cfg.warps_per_cta = warps;
+        cfg.smem_bytes = per_warp * warps;
+        cfg.stream = stream;
+        // grid: persistent CTAs; the launcher clamps to what is resident.  ctas_per_sm == 0
+        // means "as many as fit" (computed by the launcher through the occupancy API).
+        cfg.grid = ix->sm_count * (ix->ctas_per_sm ? int(ix->ctas_per_sm) : 0);
+        if (cfg.grid == 0 || exhaustive) cfg.grid = -ix->sm_count;   // negative: launcher multiplies by occupancy
+    }
 
     CUDA_TRY(cudaEventRecord(ix->ev_start, stream));
     if (exhaustive) {
@@ -697,6 +765,15 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
         ix->timed = true;
         return 0;
     }
+    if (use_fast) {
+        switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
+            case ROW_LVQ8: err = launch_search_fast<ROW_LVQ8>(op, p, cfg); break;
+            case SVSB200_F32: err = launch_search_fast<SVSB200_F32>(op, p, cfg); break;
+            case SVSB200_F16: err = launch_search_fast<SVSB200_F16>(op, p, cfg); break;
+            case SVSB200_I8: err = launch_search_fast<SVSB200_I8>(op, p, cfg); break;
+            default: err = launch_search_fast<SVSB200_U8>(op, p, cfg);
+        }
+    } else
     switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
         case ROW_LVQ8: err = launch_search<ROW_LVQ8>(op, p, cfg, nrows); break;
         case SVSB200_F32: err = launch_search<SVSB200_F32>(op, p, cfg, nrows); break;
@@ -777,11 +854,11 @@ int svsb200_last_kernel_ms(svsb200_index* ix, float* ms) {
 
 int svsb200_merge_topk_device(const uint64_t* d_ids, const float* d_dists, size_t nshards, size_t nq, size_t k, int metric,
                               uint64_t* d_out_ids, float* d_out_dists, int device, void* stream) {
-    if (nshards == 0 || nshards > 16) return fail("svsb200_merge_topk_device: 1..16 shards supported");
+    if (nshards == 0 || nshards > 1024) return fail("svsb200_merge_topk_device: 1..1024 shards supported");
     if (nq == 0 || k == 0) return 0;
     CUDA_TRY(cudaSetDevice(device));
-    const unsigned threads = 128;
-    merge_topk_kernel<<<unsigned((nq + threads - 1) / threads), threads, 0, static_cast<cudaStream_t>(stream)>>>(
+    const unsigned warps = 4;
+    merge_topk_kernel<<<unsigned((nq + warps - 1) / warps), warps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
         d_ids, d_dists, uint32_t(nshards), uint32_t(nq), uint32_t(k), metric != SVSB200_L2, d_out_ids, d_out_dists);
     count_launch();
     CUDA_TRY(cudaGetLastError());

@@ -149,6 +149,9 @@ def cuda_local_search(index, id_dtype=torch.int64):
     """Adapter: a :class:`~scalablevectorsearch_b200.Vamana` as ``local_search`` over CUDA tensors.
     Enqueues on torch's current stream; nothing synchronises."""
     np_dtype = {torch.float32: np.float32, torch.float16: np.float16, torch.int8: np.int8, torch.uint8: np.uint8}
+    if id_dtype not in (torch.int32, torch.int64):
+        raise TypeError("id_dtype must be torch.int32 or torch.int64")
+    id_bytes = 4 if id_dtype == torch.int32 else 8
 
     def run(queries: torch.Tensor, k: int):
         assert queries.is_cuda and queries.is_contiguous()
@@ -157,7 +160,7 @@ def cuda_local_search(index, id_dtype=torch.int64):
         dists = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
         if nq:
             index.search_device(queries.data_ptr(), np_dtype[queries.dtype], nq, k, ids.data_ptr(), dists.data_ptr(),
-                                stream=_stream_handle(queries.device), id_bytes=8)
+                                stream=_stream_handle(queries.device), id_bytes=id_bytes)
         return ids, dists
 
     return run

@@ -289,3 +289,8 @@ class Vamana:
 
     def set_option(self, name: str, value: int):
         _lib.check(self._lib.svsb200_set_option(self._h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        out = C.c_long()
+        _lib.check(self._lib.svsb200_get_option(self._h, name.encode(), C.byref(out)))
+        return int(out.value)

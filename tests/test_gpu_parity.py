@@ -255,3 +255,119 @@ def test_assemble_from_files_like_the_reference_binding(dataset, ref_outputs, tm
     assert ids.dtype == np.uint64 and dists.dtype == np.float32
     assert_same((ids, dists), ref_outputs["cosine_f32_f32_w100_c100_ids"], ref_outputs["cosine_f32_f32_w100_c100_dists"],
                 "assemble-from-files cosine w100")
+
+
+# ------------------------------------------------------------------------------------------------
+# round 2: the holes VERDICT r1 listed + the lean kernel against the generic one
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_fewer_than_k_reachable_matches_oracle(oracle, metric):
+    """Isolated entry point / zero-degree nodes / fewer than k reachable (tests/integration/vamana/index_search.cpp
+    never has this; the reference copies stale buffer slots, extensions.h:588-590): the kernel and the oracle pad
+    with id = all-ones and +inf (L2) / -inf (IP, cosine), and agree bit for bit on the valid prefix."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((50, 16)).astype(np.float32)
+    q = rng.standard_normal((7, 16)).astype(np.float32)
+    graph = np.zeros((50, 5), dtype=np.uint32)
+    graph[0, :3] = (2, 1, 2)      # 0 -> {1, 2}; 1 and 2 have no out-edges
+    graph[7, :2] = (1, 7)         # a self-loop elsewhere
+    for ep, nvalid in ((0, 3), (1, 1), (7, 1)):
+        index = make_index(x, graph, ep, metric)
+        want = oracle.index(x, graph, ep, metric)
+        for generic in (0, 1):
+            index.set_option("generic_kernel", generic)
+            got = search(index, q, 5, 4, 4)        # capacity 4 < k 5 -> both become 5 (index.h:590-592)
+            wi, wd = want.search(q, 5, 4, 4)
+            assert_same(got, wi, wd, f"{metric} ep{ep} generic{generic}")
+            assert np.all(got[0][:, nvalid:] == np.uint64(0xFFFFFFFFFFFFFFFF))
+            pad = got[1][:, nvalid:]
+            assert np.all(np.isposinf(pad) if metric == "l2" else np.isneginf(pad))
+
+
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
+def test_lean_and_generic_kernels_agree(dataset, oracle, metric):
+    """Every configuration the lean kernel takes gives the generic kernel's bits (and both the oracle's): window
+    past one 128-entry block, split buffer, tiny window, wide graph rows (128 neighbours = 4 register words)."""
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, metric)
+    want = oracle.index(dataset.data, dataset.graph, dataset.entry_point, metric)
+    q = dataset.queries[:192]
+    for window, cap, k in ((1, 1, 1), (10, 10, 10), (33, 97, 20), (128, 128, 10), (130, 300, 50), (300, 300, 100)):
+        wi, wd = want.search(q, k, window, cap)
+        for generic in (0, 1):
+            index.set_option("generic_kernel", generic)
+            got = search(index, q, k, window, cap)
+            assert index.get_option("last_kernel") == 1 - generic
+            assert_same(got, wi, wd, f"{metric} w{window} c{cap} generic{generic}")
+
+
+def test_configurations_outside_the_lean_kernel_fall_back(oracle):
+    """max_degree > 128 and filter-off runs take the generic kernel; same bits as the oracle either way."""
+    rng = np.random.default_rng(11)
+    n, dim = 1200, 32
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((64, dim)).astype(np.float32)
+    graph = knn_graph(x, 140, rng)
+    index = make_index(x, graph, 1, "l2")
+    wi, wd = oracle.index(x, graph, 1, "l2").search(q, 10, 40, 64)
+    assert_same(search(index, q, 10, 40, 64), wi, wd, "R140")
+    assert index.get_option("last_kernel") == 0
+    graph64 = knn_graph(x, 64, rng)
+    index = make_index(x, graph64, 1, "l2")
+    wi, wd = oracle.index(x, graph64, 1, "l2").search(q, 10, 40, 64)
+    assert_same(search(index, q, 10, 40, 64), wi, wd, "R64 lean")
+    assert index.get_option("last_kernel") == 1
+    index.set_option("visited_filter_slots", 0)
+    assert_same(search(index, q, 10, 40, 64), wi, wd, "R64 filter off")
+    assert index.get_option("last_kernel") == 0
+    from scalablevectorsearch_b200 import Svsb200Error
+    with pytest.raises(Svsb200Error):
+        index.set_option("visited_filter_slots", 4)     # would break the 16-byte alignment of the arrays behind it
+
+
+@pytest.mark.parametrize("id_bytes", [4, 8])
+def test_search_device_matches_host_path(dataset, ref_outputs, id_bytes):
+    """svsb200_search_device (device-resident buffers, caller's stream; the path bench.py times as `value`)."""
+    import torch
+    from scalablevectorsearch_b200 import SearchBufferConfig
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    index.search_parameters.buffer_config = SearchBufferConfig(22, 23)
+    q = torch.from_numpy(dataset.queries[100:]).cuda()
+    ids = torch.empty((900, 10), dtype=torch.int32 if id_bytes == 4 else torch.int64, device="cuda")
+    dists = torch.empty((900, 10), dtype=torch.float32, device="cuda")
+    index.search_device(q.data_ptr(), np.float32, 900, 10, ids.data_ptr(), dists.data_ptr(),
+                        stream=torch.cuda.current_stream().cuda_stream or 1, id_bytes=id_bytes)
+    torch.cuda.synchronize()
+    assert_same((ids.cpu().numpy(), dists.cpu().numpy()), ref_outputs["l2_f32_f32_w22_c23_ids"],
+                ref_outputs["l2_f32_f32_w22_c23_dists"], f"search_device id_bytes={id_bytes}")
+
+
+@pytest.mark.parametrize("greater", [False, True])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_merge_topk_device_is_the_total_order(shards, greater):
+    """svsb200_merge_topk_device == sort of all shards' candidates by TotalOrder (distance, then id;
+    lib/neighbor.h:143-155), with exact ties across and INSIDE shards (a shard's list is in insertion order,
+    not id order), -1 padding and short lists."""
+    import torch
+    from scalablevectorsearch_b200.multi_gpu import cuda_merge, merge_topk_reference_order
+    rng = np.random.default_rng(shards * 2 + greater)
+    nq, k = 257, 10
+    ids = np.full((shards, nq, k), -1, dtype=np.int64)
+    dists = np.zeros((shards, nq, k), dtype=np.float32)
+    sign = -1.0 if greater else 1.0
+    for s in range(shards):
+        for q in range(nq):
+            m = int(rng.integers(0, k + 1))                          # short lists, sometimes empty
+            d = np.sort(rng.integers(0, 4, size=m).astype(np.float32))    # 4 distinct values: ties everywhere
+            if q % 7 == 0:
+                d = d * 0.0 - (0.0 if q % 14 else 0.0)               # all-equal rows
+            if q % 11 == 0 and m:
+                d[0] = -0.0                                            # -0 == +0 under operator<
+            pool = rng.permutation(1000)[:m] + 1000 * s               # shard-disjoint ids, NOT sorted inside ties
+            ids[s, q, :m] = pool
+            dists[s, q, :m] = sign * d
+            dists[s, q, m:] = -np.inf if greater else np.inf
+    want_i, want_d = merge_topk_reference_order(ids, dists, k, greater)
+    got_i, got_d = cuda_merge(torch.from_numpy(ids).cuda(), torch.from_numpy(dists).cuda(), k, greater)
+    torch.cuda.synchronize()
+    assert np.array_equal(got_i.cpu().numpy(), want_i)
+    assert np.array_equal(got_d.cpu().numpy() + 0.0, want_d + 0.0)   # +0.0: -0 and +0 compare equal

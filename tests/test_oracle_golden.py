@@ -101,7 +101,7 @@ def test_oracle_edge_cases(oracle):
     graph[0, :3] = (2, 1, 2)      # 0 -> {1, 2}; 1 and 2 have no out-edges
     idx = oracle.index(x, graph, 0, "l2")
     ids, dists = idx.search(q, 5, 4, 4)          # capacity 4 < k 5  -> both become 5
-    assert np.all(ids[:, 3:] == 0xFFFFFFFF) and np.all(np.isnan(dists[:, 3:]))
+    assert np.all(ids[:, 3:] == np.uint64(0xFFFFFFFFFFFFFFFF)) and np.all(np.isposinf(dists[:, 3:]))
     assert np.all(np.sort(ids[:, :3], axis=1) == np.array([0, 1, 2]))
     assert np.all(np.diff(dists[:, :3], axis=1) >= 0)
     with pytest.raises(RuntimeError):
