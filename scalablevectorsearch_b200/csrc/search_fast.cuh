@@ -46,19 +46,19 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
     const int t = lane % G;
     const unsigned lt_mask = (1u << lane) - 1u;
 
-    const uint32_t fwords = p.filter_slots / 2;   // 16-bit tags, two per word (the host routes other filter modes to the generic kernel)
-    uint32_t* filt = reinterpret_cast<uint32_t*>(smem_raw);                  // [fwords] visited filter
-    float* q_s = reinterpret_cast<float*>(filt + ((fwords + 3u) & ~3u));     // [qstride] prepared query
+    // Visited filter: `fsets` sets of eight 16-bit tags (one 128-bit word per set, newest tag first).  Set index
+    // + tag reconstruct the full id, so a hit is exact (the host guarantees (n-1) >> filter_shift < 0xFFFF).
+    const uint32_t fsets = p.filter_slots / 8;
+    uint4* filt = reinterpret_cast<uint4*>(smem_raw);                        // [fsets]
+    float* q_s = reinterpret_cast<float*>(filt + fsets);                     // [qstride] prepared query
     uint2* buf = reinterpret_cast<uint2*>(q_s + p.qstride);                  // [cap_pad] {key bits, id | visited}
     float* ckey = reinterpret_cast<float*>(buf + p.cap_pad);                 // [deg_pad] candidate keys
     uint32_t* cid = reinterpret_cast<uint32_t*>(ckey + p.deg_pad);           // [deg_pad] candidate ids
-    uint2* sst = reinterpret_cast<uint2*>(cid + p.deg_pad);                  // [32] a group's survivors, sorted
-    float* skc = reinterpret_cast<float*>(sst + 32);                         // [32+4] their keys in adjacency order
 
     const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
     const uint32_t C = p.capacity, W = p.window;
     const char* vectors = reinterpret_cast<const char*>(p.vectors);
-    const uint32_t fmask = fwords - 1u;             // set index mask (fwords is a power of two)
+    const uint32_t fmask = fsets - 1u;              // set index mask (fsets is a power of two)
 
     for (;;) {
         uint32_t q = 0;
@@ -81,11 +81,8 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
             for (uint32_t i = lane; i < p.qstride / 4; i += 32) dst[i] = __ldg(src + i);
         }
         const float aux0 = p.qaux[2 * size_t(q)], aux1 = p.qaux[2 * size_t(q) + 1];
-        {
-            uint4* f4 = reinterpret_cast<uint4*>(filt);
 #pragma unroll 4
-            for (uint32_t i = lane; i < fwords / 4; i += 32) f4[i] = make_uint4(NONE, NONE, NONE, NONE);
-        }
+        for (uint32_t i = lane; i < fsets; i += 32) filt[i] = make_uint4(NONE, NONE, NONE, NONE);
         // ---- EntryPointInitializer (greedy_search.h:62-94): the entry point goes through the same
         // evaluate-and-merge code as a hop's neighbours, into the empty buffer ----
         uint32_t size = 0, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
@@ -129,21 +126,23 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
             }
             if (!found) break;   // done()
             const uint32_t node = buf[pos].y;
-            // graph.get_node(node): staged in registers by the previous hop if the prediction held
-            uint32_t nb[kFastMaxGW];
-            {
-                const bool have = (node == staged_node);
+            // graph.get_node(node): staged in registers by the previous hop if the prediction held; a miss
+            // loads into the same registers.  nb[] is copied out BEFORE the next prefetch is issued into nxt[]:
+            // the write-after-read dependence keeps the prefetch loads behind every wait on this hop's row, so
+            // their latency is never waited for here (they have a whole hop to land).
+            if (node != staged_node) {
                 const uint32_t* grow = p.graph + size_t(node) * p.gstride;
 #pragma unroll
                 for (int w = 0; w < kFastMaxGW; ++w) {
-                    nb[w] = kNoNeighbor;
                     if (w * 32u < p.gstride) {
                         const uint32_t j = w * 32u + lane;
-                        if (have) nb[w] = nxt[w];
-                        else if (j < p.gstride) nb[w] = __ldg(grow + j);
+                        nxt[w] = (j < p.gstride) ? __ldg(grow + j) : kNoNeighbor;
                     }
                 }
             }
+            uint32_t nb[kFastMaxGW];
+#pragma unroll
+            for (int w = 0; w < kFastMaxGW; ++w) nb[w] = nxt[w];
             staged_node = NONE;
             if (pred_pos != NONE) {
                 staged_node = buf[pred_pos].y & kIdMask;
@@ -167,13 +166,19 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
                 if (w * 32u < p.gstride) {
                     bool fresh = nb[w] != kNoNeighbor;
                     if (fresh) {   // the filter is always on here (the host routes filter-off runs to the generic kernel)
-                        // two-way set-associative, LRU by position: one 32-bit word holds two 16-bit tags
-                        // (set index + tag reconstruct the full id, so a hit is exact)
                         const uint32_t slot = nb[w] & fmask;
                         const uint32_t tag = nb[w] >> p.filter_shift;
-                        const uint32_t set = filt[slot];
-                        fresh = ((set & 0xFFFFu) != tag) && ((set >> 16) != tag);
-                        if (fresh) filt[slot] = (set << 16) | tag;
+                        const uint32_t tag2 = tag * 0x00010001u;
+                        const uint4 set = filt[slot];
+                        // any 16-bit half of the set equal to the tag?  x ^ tag2 has a zero half exactly then;
+                        // (v - 0x00010001) & ~v & 0x80008000 is non-zero iff v has a zero half.
+                        const uint32_t x0 = set.x ^ tag2, x1 = set.y ^ tag2, x2 = set.z ^ tag2, x3 = set.w ^ tag2;
+                        const uint32_t hit = (((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) |
+                                              ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3)) & 0x80008000u;
+                        fresh = hit == 0u;
+                        if (fresh)   // push the new tag in front, drop the oldest
+                            filt[slot] = make_uint4((set.x << 16) | tag, __funnelshift_l(set.x, set.y, 16),
+                                                    __funnelshift_l(set.y, set.z, 16), __funnelshift_l(set.z, set.w, 16));
                     }
                     const unsigned m = __ballot_sync(FULL, fresh);
                     if (fresh) cid[ncand + __popc(m & lt_mask)] = nb[w];
@@ -197,7 +202,7 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
             // neighbour expansion: distance of every fresh neighbour (greedy_search.h:190-201)
 #pragma unroll 1
             for (uint32_t base = 0; base < ncand; base += NROWS * GROUPS)
-                eval_pass<ROWT, OP, DS, NROWS, KS>(p, q_s, vectors, cid, ckey, base, ncand, g, t, aux0, aux1, ksign);
+                eval_pass<ROWT, OP, DS, NROWS, KS, true>(p, q_s, vectors, cid, ckey, base, ncand, g, t, aux0, aux1, ksign);
             __syncwarp();
 
             // ---- merge, 32 candidates at a time (each group == its sequential inserts) ----
@@ -237,6 +242,10 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
                 const uint32_t S = __popc(m);
                 // stable rank among the survivors: (key, adjacency order).  Their keys are compacted (adjacency
                 // order) into skc[], padded with +inf, and every survivor counts the ones ordered before it.
+                // (the group's own 32 candidate slots are dead once d / id sit in registers: they hold the
+                // compacted keys first and the sorted survivors afterwards)
+                float* skc = ckey + r0;
+                uint32_t* sid = cid + r0;
                 const uint32_t t_me = __popc(m & lt_mask);
                 skc[lane] = INFINITY;
                 __syncwarp();
@@ -255,7 +264,11 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
                 // final position = insertion point + rank; unique per survivor and increasing in rank
                 const uint32_t fp = surv ? ipos + rank : NONE;
                 const uint32_t minpos = __reduce_min_sync(FULL, surv ? ipos : NONE);
-                if (surv) sst[rank] = make_uint2(__float_as_uint(d), id);
+                __syncwarp();   // every lane is done reading the compacted keys
+                if (surv) {
+                    skc[rank] = d;
+                    sid[rank] = id;
+                }
                 const uint32_t newsize = min(size + S, C);
                 const int top = int((newsize - 1) >> 5), lo = int(minpos >> 5);
                 // Final slot f holds either the survivor with fp == f or the old entry f - #{fp < f}.  Done in
@@ -280,7 +293,7 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
                             const uint32_t before = S - (above + __popc(Ms >> lane));   // survivors with fp < f
                             const bool mine = (Ms >> lane) & 1u;
                             wr[u] = (f < newsize) && (f >= minpos);
-                            if (wr[u]) e[u] = mine ? sst[before] : buf[f - before];
+                            if (wr[u]) e[u] = mine ? make_uint2(__float_as_uint(skc[before]), sid[before]) : buf[f - before];
                         }
                         above += __popc(Ms);
                     }

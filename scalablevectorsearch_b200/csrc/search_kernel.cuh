@@ -169,7 +169,7 @@ template <int LPT> __device__ __forceinline__ float reduce_lanes(float (&s)[LPT]
 //   t         thread index inside the group
 // Returns the *raw* reduced sums (op, norm) -- identical in every thread of the group.
 // ---------------------------------------------------------------------------------------
-template <int ROWT, int OP, int DS, int NROWS>
+template <int ROWT, int OP, int DS, int NROWS, bool DENSE = false>
 __device__ __forceinline__ void float_rows(
     const SearchParams& p, const float* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
     float (&sum)[NROWS], float (&nrm)[NROWS]) {
@@ -184,7 +184,7 @@ __device__ __forceinline__ void float_rows(
         for (int r = 0; r < NROWS; ++r) {
             lvq_delta[r] = 0.f;
             lvq_lower[r] = 0.f;
-            if (rowp[r]) {
+            if (DENSE || rowp[r]) {
                 const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rowp[r] + p.lvq_const_offset));
                 const __half2 h = *reinterpret_cast<const __half2*>(&c);
                 lvq_delta[r] = __low2float(h);
@@ -224,7 +224,7 @@ __device__ __forceinline__ void float_rows(
         for (int r = 0; r < NROWS; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (rowp[r]) raw[r][k] = R::load(rowp[r] + size_t(base + 16 * k + thread_elem) * R::ESIZE);
+                if (DENSE || rowp[r]) raw[r][k] = R::load(rowp[r] + size_t(base + 16 * k + thread_elem) * R::ESIZE);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             float x[LPT];
@@ -235,7 +235,7 @@ __device__ __forceinline__ void float_rows(
             }
 #pragma unroll
             for (int r = 0; r < NROWS; ++r) {
-                if (!rowp[r]) continue;
+                if (!DENSE && !rowp[r]) continue;
                 float y[LPT];
                 R::cvt(raw[r][k], y);
 #pragma unroll
@@ -265,7 +265,7 @@ __device__ __forceinline__ void float_rows(
         for (int r = 0; r < NROWS; ++r)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                if (rowp[r] && base + 16 * k + thread_elem < D)
+                if ((DENSE || rowp[r]) && base + 16 * k + thread_elem < D)
                     raw[r][k] = R::load(rowp[r] + size_t(base + 16 * k + thread_elem) * R::ESIZE);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -279,7 +279,7 @@ __device__ __forceinline__ void float_rows(
                 }
 #pragma unroll
                 for (int r = 0; r < NROWS; ++r) {
-                    if (!rowp[r]) continue;
+                    if (!DENSE && !rowp[r]) continue;
                     float y[LPT];
                     R::cvt(raw[r][k], y);
 #pragma unroll
@@ -318,7 +318,7 @@ __device__ __forceinline__ void float_rows(
 // finer-grained passes when only a handful of (large) rows pass the visited filter.
 // Same expression tree, same bits.
 // ---------------------------------------------------------------------------------------
-template <int ROWT, int OP, int NROWS>
+template <int ROWT, int OP, int NROWS, bool DENSE = false>
 __device__ __forceinline__ void float_rows_split(
     const SearchParams& p, const float* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
     float (&sum)[NROWS], float (&nrm)[NROWS]) {
@@ -335,7 +335,7 @@ __device__ __forceinline__ void float_rows_split(
         for (int r = 0; r < NROWS; ++r) {
             lvq_delta[r] = 0.f;
             lvq_lower[r] = 0.f;
-            if (rowp[r]) {
+            if (DENSE || rowp[r]) {
                 const uint32_t c = __ldg(reinterpret_cast<const uint32_t*>(rowp[r] + p.lvq_const_offset));
                 const __half2 h = *reinterpret_cast<const __half2*>(&c);
                 lvq_delta[r] = __low2float(h);
@@ -370,7 +370,7 @@ __device__ __forceinline__ void float_rows_split(
         }
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
-            if (!rowp[r]) continue;
+            if (!DENSE && !rowp[r]) continue;
             float y[LPT];
             R::cvt(raw[r], y);
 #pragma unroll
@@ -393,7 +393,7 @@ __device__ __forceinline__ void float_rows_split(
         for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int r = 0; r < NROWS; ++r)
-                if (rowp[r]) raw[u][r] = R::load(rowp[r] + size_t((b + u) * 64 + 16 * kk + thread_elem) * R::ESIZE);
+                if (DENSE || rowp[r]) raw[u][r] = R::load(rowp[r] + size_t((b + u) * 64 + 16 * kk + thread_elem) * R::ESIZE);
 #pragma unroll
         for (int u = 0; u < 4; ++u) step(raw[u], (b + u) * 64 + 16 * kk + thread_elem, D);
     }
@@ -401,7 +401,7 @@ __device__ __forceinline__ void float_rows_split(
         typename R::raw_t raw[NROWS];
 #pragma unroll
         for (int r = 0; r < NROWS; ++r)
-            if (rowp[r]) raw[r] = R::load(rowp[r] + size_t(b * 64 + 16 * kk + thread_elem) * R::ESIZE);
+            if (DENSE || rowp[r]) raw[r] = R::load(rowp[r] + size_t(b * 64 + 16 * kk + thread_elem) * R::ESIZE);
         step(raw, b * 64 + 16 * kk + thread_elem, D);
     }
     if (nblk > 0) {
@@ -427,7 +427,7 @@ __device__ __forceinline__ void float_rows_split(
         const int e0 = e + thread_elem;
 #pragma unroll
         for (int r = 0; r < NROWS; ++r)
-            if (rowp[r] && e0 < D) raw[r] = R::load(rowp[r] + size_t(e0) * R::ESIZE);
+            if ((DENSE || rowp[r]) && e0 < D) raw[r] = R::load(rowp[r] + size_t(e0) * R::ESIZE);
         if (e0 < D) step(raw, e0, D);
     }
 #pragma unroll
@@ -447,7 +447,7 @@ __device__ __forceinline__ void float_rows_split(
 
 // Exact integer sums for (int8,int8)/(uint8,uint8): groups of 4 threads, 16-byte loads,
 // dp4a.  Order-free (integer), so any lane split is bit-exact.
-template <int ROWT, int NROWS>
+template <int ROWT, int NROWS, bool DENSE = false>
 __device__ __forceinline__ void int_rows(
     const SearchParams& p, const uint8_t* __restrict__ q_s, const char* const (&rowp)[NROWS], int t,
     int (&xy)[NROWS], int (&yy)[NROWS]) {
@@ -462,7 +462,7 @@ __device__ __forceinline__ void int_rows(
         const uint32_t qw[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
         for (int r = 0; r < NROWS; ++r) {
-            if (!rowp[r]) continue;
+            if (!DENSE && !rowp[r]) continue;
             uint4 rv = __ldg(reinterpret_cast<const uint4*>(rowp[r] + 16 * v));
             const uint32_t rw[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
@@ -516,7 +516,7 @@ __device__ __forceinline__ float finish_distance(const SearchParams& p, float su
 // One pass of the neighbour expansion: NR rows per thread group, GROUPS groups per warp.
 // Candidate `base + r*GROUPS + g` is evaluated by group g in slot r; thread 0 of the group
 // publishes the sort key into ckey[].
-template <int ROWT, int OP, int DS, int NR, int KS = 1>
+template <int ROWT, int OP, int DS, int NR, int KS = 1, bool DENSE = false>
 __device__ __forceinline__ void eval_pass(const SearchParams& p, const float* q_s, const char* vectors,
                                           const uint32_t* cid, float* ckey, uint32_t base, uint32_t count, int g, int t,
                                           float aux0, float aux1, float ksign) {
@@ -528,22 +528,28 @@ __device__ __forceinline__ void eval_pass(const SearchParams& p, const float* q_
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         idx[r] = base + r * GROUPS + g;
-        rowp[r] = idx[r] < count ? vectors + size_t(cid[idx[r]]) * p.row_stride : nullptr;
+        if constexpr (DENSE) {
+            // slots past the last candidate re-read the last candidate's row (already in flight in this
+            // pass) instead of being predicated off: no null checks, no predicated arithmetic
+            rowp[r] = vectors + size_t(cid[min(idx[r], count - 1)]) * p.row_stride;
+        } else {
+            rowp[r] = idx[r] < count ? vectors + size_t(cid[idx[r]]) * p.row_stride : nullptr;
+        }
     }
     float sum[NR], nrm[NR];
     int ixy[NR], iyy[NR];
     if constexpr (kInt) {
-        int_rows<ROWT, NR>(p, reinterpret_cast<const uint8_t*>(q_s), rowp, t, ixy, iyy);
+        int_rows<ROWT, NR, DENSE>(p, reinterpret_cast<const uint8_t*>(q_s), rowp, t, ixy, iyy);
     } else if constexpr (KS == 4) {
-        float_rows_split<ROWT, OP, NR>(p, q_s, rowp, t, sum, nrm);
+        float_rows_split<ROWT, OP, NR, DENSE>(p, q_s, rowp, t, sum, nrm);
     } else {
-        float_rows<ROWT, OP, DS, NR>(p, q_s, rowp, t, sum, nrm);
+        float_rows<ROWT, OP, DS, NR, DENSE>(p, q_s, rowp, t, sum, nrm);
     }
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
         const float d = finish_distance<OP>(p, kInt ? 0.f : sum[r], (OP == OP_COSF) ? nrm[r] : 0.f, kInt ? ixy[r] : 0,
                                             kInt ? iyy[r] : 0, aux0, aux1);
-        if (t == 0 && rowp[r]) ckey[idx[r]] = __fmul_rn(d, ksign);
+        if (t == 0 && (DENSE ? idx[r] < count : rowp[r] != nullptr)) ckey[idx[r]] = __fmul_rn(d, ksign);
     }
 }
 

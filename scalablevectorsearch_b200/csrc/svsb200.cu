@@ -726,13 +726,26 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     // The lean kernel (search_fast.cuh) covers the common shape: 16-bit-tag filter on, adjacency rows of up to
     // 128 neighbours; anything else (and the exhaustive scan) runs on the generic kernel.
     const uint32_t fast_cap_pad = uint32_t(round_up(capacity, 32));
-    const size_t fast_bytes = fast_smem_bytes(p.qstride, fast_cap_pad, p.deg_pad, p.filter_slots * 2u);
-    const bool use_fast = !exhaustive && !ix->generic_kernel && p.filter_slots >= 8 && p.filter_tag16 &&
-                          p.deg_pad <= 32u * kFastMaxGW && fast_bytes <= smem_limit;
+    // its filter: sets of eight 16-bit tags; default 256 sets (4 KB), more when n needs it for exactness
+    uint32_t fast_slots = ix->filter_slots < 0 ? 2048u : uint32_t(ix->filter_slots);
+    if (fast_slots && fast_slots < 64) fast_slots = 64;
+    uint32_t fast_shift = 0;
+    while ((8u << fast_shift) < fast_slots) ++fast_shift;                       // log2(sets)
+    while (fast_slots && (uint64_t(ix->n - 1) >> fast_shift) >= 0xFFFFull && fast_shift < 20) {
+        ++fast_shift;
+        fast_slots <<= 1;
+    }
+    const size_t fast_bytes = fast_smem_bytes(p.qstride, fast_cap_pad, p.deg_pad, fast_slots * 2u);
+    const bool use_fast = !exhaustive && !ix->generic_kernel && fast_slots >= 64 && ix->filter_tag16 &&
+                          (uint64_t(ix->n - 1) >> fast_shift) < 0xFFFFull && p.deg_pad <= 32u * kFastMaxGW &&
+                          fast_bytes <= smem_limit;
     ix->last_kernel = use_fast ? 1 : 0;
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
     if (use_fast) {
         p.cap_pad = fast_cap_pad;
+        p.filter_slots = fast_slots;
+        p.filter_shift = fast_shift;
+        p.filter_tag16 = 1;
         cfg.warps_per_cta = 1;
         cfg.smem_bytes = fast_bytes;
         cfg.stream = stream;
