@@ -27,12 +27,20 @@
 
 namespace svsb200 {
 
-#ifndef SVSB200_FAST_MIN_BLOCKS
-#define SVSB200_FAST_MIN_BLOCKS 16
+// Resident CTAs (= warps = queries) per SM the compiler must allow for: 24 (80 registers) where the
+// instantiation fits without spilling, 16 (128 registers) otherwise (ptxas -v, csrc/*.ptxas.log).
+template <int ROWT, int OP, int DS, int KS> constexpr int fast_min_blocks() {
+#ifdef SVSB200_FAST_MIN_BLOCKS
+    return SVSB200_FAST_MIN_BLOCKS;
+#else
+    if (ROWT == SVSB200_F32 && (DS != 0 || KS == 4)) return 24;
+    if (ROWT == SVSB200_F16 && DS == 96 && OP != OP_COSF) return 24;
+    return 16;
 #endif
+}
 
 template <int ROWT, int OP, int DS, int KS>
-__global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fast_kernel(const __grid_constant__ SearchParams p) {
+__global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vamana_search_fast_kernel(const __grid_constant__ SearchParams p) {
     constexpr int NROWS = 2;
     constexpr bool kInt = (OP >= OP_L2I);
     constexpr int G = kInt ? 4 : KS * 16 / Row<ROWT>::LPT;   // threads per row
@@ -133,12 +141,8 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
             if (node != staged_node) {
                 const uint32_t* grow = p.graph + size_t(node) * p.gstride;
 #pragma unroll
-                for (int w = 0; w < kFastMaxGW; ++w) {
-                    if (w * 32u < p.gstride) {
-                        const uint32_t j = w * 32u + lane;
-                        nxt[w] = (j < p.gstride) ? __ldg(grow + j) : kNoNeighbor;
-                    }
-                }
+                for (int w = 0; w < kFastMaxGW; ++w)
+                    if (w * 32u < p.gstride) nxt[w] = __ldg(grow + w * 32u + lane);   // gstride % 32 == 0 here
             }
             uint32_t nb[kFastMaxGW];
 #pragma unroll
@@ -148,12 +152,8 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
                 staged_node = buf[pred_pos].y & kIdMask;
                 const uint32_t* prow = p.graph + size_t(staged_node) * p.gstride;
 #pragma unroll
-                for (int w = 0; w < kFastMaxGW; ++w) {
-                    if (w * 32u < p.gstride) {
-                        const uint32_t j = w * 32u + lane;
-                        nxt[w] = (j < p.gstride) ? __ldg(prow + j) : kNoNeighbor;
-                    }
-                }
+                for (int w = 0; w < kFastMaxGW; ++w)
+                    if (w * 32u < p.gstride) nxt[w] = __ldg(prow + w * 32u + lane);
             }
             if (lane == 0) buf[pos].y = node | kVisitedBit;
             cursor = pos + 1;
@@ -200,9 +200,18 @@ __global__ void __launch_bounds__(32, SVSB200_FAST_MIN_BLOCKS) vamana_search_fas
             }
 
             // neighbour expansion: distance of every fresh neighbour (greedy_search.h:190-201)
+            // (two rows per thread group while more than GROUPS candidates remain, one row for the rest:
+            // 69% of the hops of the C2 workload have at most 8 fresh neighbours)
 #pragma unroll 1
-            for (uint32_t base = 0; base < ncand; base += NROWS * GROUPS)
-                eval_pass<ROWT, OP, DS, NROWS, KS, true>(p, q_s, vectors, cid, ckey, base, ncand, g, t, aux0, aux1, ksign);
+            for (uint32_t base = 0; base < ncand;) {
+                if (ncand - base > uint32_t(GROUPS)) {
+                    eval_pass<ROWT, OP, DS, NROWS, KS, true>(p, q_s, vectors, cid, ckey, base, ncand, g, t, aux0, aux1, ksign);
+                    base += NROWS * GROUPS;
+                } else {
+                    eval_pass<ROWT, OP, DS, 1, KS, true>(p, q_s, vectors, cid, ckey, base, ncand, g, t, aux0, aux1, ksign);
+                    base += GROUPS;
+                }
+            }
             __syncwarp();
 
             // ---- merge, 32 candidates at a time (each group == its sequential inserts) ----

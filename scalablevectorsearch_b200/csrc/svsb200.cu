@@ -462,7 +462,9 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
     }
     const size_t src_stride = row_stride_bytes ? row_stride_bytes : row_bytes;
     ix->row_stride = uint32_t(storage == SVSB200_LVQ8 ? svsb200_lvq8_row_stride(dim) : round_up(row_bytes, 16));
-    ix->gstride = uint32_t(round_up(ix->max_degree, 4));
+    // rows of up to 128 neighbours are padded to whole 32-word groups (one coalesced load per group and lane in
+    // the lean kernel, no per-lane bounds checks); wider rows stay 16-byte aligned only
+    ix->gstride = uint32_t(round_up(ix->max_degree, ix->max_degree <= 32u * kFastMaxGW ? 32 : 4));
 
     auto cleanup = [&](int rc) {
         svsb200_index_destroy(ix);
@@ -738,6 +740,7 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     const size_t fast_bytes = fast_smem_bytes(p.qstride, fast_cap_pad, p.deg_pad, fast_slots * 2u);
     const bool use_fast = !exhaustive && !ix->generic_kernel && fast_slots >= 64 && ix->filter_tag16 &&
                           (uint64_t(ix->n - 1) >> fast_shift) < 0xFFFFull && p.deg_pad <= 32u * kFastMaxGW &&
+                          p.gstride % 32u == 0 &&
                           fast_bytes <= smem_limit;
     ix->last_kernel = use_fast ? 1 : 0;
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
