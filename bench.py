@@ -196,16 +196,25 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
-        "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(workload_config(args.workload, w, graph), global_batch=w["nq"] * (1 if args.strong else args.gpus),
-                       batch_per_gpu=w["nq"] // (args.gpus if args.strong else 1)),
+        "scaling": "weak" if args.weak else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": run_config(args.workload, w, graph, args.gpus, args.weak),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "reference",
                          "sample": f"full {w['nq']}-query batch x {len(times)} steps, {threads} threads = container CPU quota "
-                                   f"(os.cpu_count()={os.cpu_count()}), "
-                                   f"avx512={ref.avx512()}"},
+                                   f"(os.cpu_count()={os.cpu_count()}), avx512={ref.avx512()}, "
+                                   f"{REF_PAGES}"},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+REF_PAGES = ("reference data+graph in lib::Allocator memory = 4 KiB pages (transparent hugepages per the host's THP "
+             "setting); its HugepageAllocator (core/allocator.h:94-150) is not used by this arm")
+
+
+def run_config(name, w, graph, gpus, weak):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    return dict(workload_config(name, w, graph), global_batch=w["nq"] * (gpus if weak else 1),
+                batch_per_gpu=w["nq"] if weak else -(-w["nq"] // gpus))
 
 
 def workload_config(name, w, graph):
@@ -263,105 +272,130 @@ def run_ours(args):
         name, val = kv.split("=")
         index.set_option(name, int(val))
     lib = _lib.lib()
-    # Weak scaling (default, SURVEY.md 8e mode A): every GPU keeps the metric's own batch (10 000 queries), the
-    # global batch is N x that; rank r owns query block r (block 0 == the single-GPU batch).  --strong keeps the
-    # global batch at the single-GPU size and splits it, which under-fills 8 B200s (1 250 queries each).
-    weak = world > 1 and not args.strong
-    if weak:
-        from scalablevectorsearch_b200.synthetic import clustered_queries
-        queries = np.concatenate([queries] + [clustered_queries(w["nq"], w["dim"], r) for r in range(1, world)])
-    nq, k = queries.shape[0], w["k"]
-    q_host = torch.from_numpy(queries).pin_memory()
-    q_dev = q_host.to(dev, non_blocking=True)
-    searcher = ReplicatedSearch(cuda_local_search(index))
+    k = w["k"]
+    searcher = ReplicatedSearch(cuda_local_search(index, id_dtype=torch.int32), id_dtype=torch.int32)
+
+    # Two batch shapes (SURVEY.md 8e mode A).  STRONG -- the metric's own configuration: ONE batch of w["nq"] queries
+    # split over the GPUs with threads::balance; this is `value`.  WEAK: every GPU keeps a whole w["nq"]-query batch
+    # (global batch N x that; block 0 is the single-GPU batch), reported beside it under "weak".
+    from scalablevectorsearch_b200.synthetic import clustered_queries
+    q_strong = queries
+    q_weak = queries if world == 1 else np.concatenate(
+        [queries] + [clustered_queries(w["nq"], w["dim"], r) for r in range(1, world)])
+
+    def time_mode(q_np):
+        """W warm-ups, K timed steps of the device-resident multi-GPU search (local search -> one NCCL all-gather of
+        the result rows), CUDA events on this rank's stream, max over ranks."""
+        q_dev = torch.from_numpy(q_np).to(dev)
+        for _ in range(max(args.warmup, 3)):
+            out = searcher.search(q_dev, k)
+        torch.cuda.synchronize()
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.svsb200_launch_count()
+        start.record()
+        for _ in range(args.steps):
+            out = searcher.search(q_dev, k)
+        stop.record()
+        torch.cuda.synchronize()
+        launched = lib.svsb200_launch_count() - l0
+        barrier()
+        ms = start.elapsed_time(stop)
+        kern = []
+        for _ in range(3):
+            searcher.search(q_dev, k)
+            torch.cuda.synchronize()
+            kern.append(index.last_kernel_ms())
+        t = torch.tensor([ms, float(np.mean(kern))], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), out, q_dev, launched
+
+    # ---- per-query work counters (reference tracker equivalents) for the roofline, on the strong batch ----
+    nq = q_strong.shape[0]
     lo, hi = balance(nq, world, rank)
-
-    def step_device():
-        return searcher.search(q_dev, k)
-
-    # ---- per-query work counters (reference tracker equivalents) for the roofline ----
+    q_dev = torch.from_numpy(q_strong).to(dev)
     index.set_counting(True)
-    ids_all, d_all = step_device()
+    searcher.search(q_dev, k)
     torch.cuda.synchronize()
     hops, evals = index.counters(hi - lo)
     fetched = index.fetched(hi - lo)
     index.set_counting(False)
     qb = w["dim"] * queries.dtype.itemsize
     shard_bytes, bytes_per_query = algorithmic_bytes(hops, evals, fetched, w, row_bytes, qb)
-    _, ref_bytes_per_query = algorithmic_bytes(hops, evals, evals, w, row_bytes, qb)
+    shard_ref_bytes, ref_bytes_per_query = algorithmic_bytes(hops, evals, evals, w, row_bytes, qb)
 
-    # ---- device-resident timing: W warm-ups, K timed steps, CUDA events, max over ranks ----
-    for _ in range(max(args.warmup, 3) - 1):
-        step_device()
-    torch.cuda.synchronize()
-    barrier()
-    launches0 = lib.svsb200_launch_count()
-    kernel_ms = []
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clocks:
-        torch.cuda.synchronize()
-        start.record()
-        for _ in range(args.steps):
-            ids_all, d_all = step_device()
-            if args.steps <= 64:
-                pass
-        stop.record()
-        torch.cuda.synchronize()
-    barrier()
-    launches = lib.svsb200_launch_count() - launches0
-    elapsed_ms = start.elapsed_time(stop)
-    # search-kernel duration: CUDA events recorded by the library around the kernel on the same stream
-    for _ in range(3):
-        step_device()
-        torch.cuda.synchronize()
-        kernel_ms.append(index.last_kernel_ms())
+        elapsed_ms, kern_ms, (ids_all, d_all), q_dev, launches = time_mode(q_strong)
+    qps = nq * args.steps / (elapsed_ms * 1e-3)
+    weak = None
+    if world > 1:
+        w_ms, w_kern, _, _, _ = time_mode(q_weak)
+        weak = {"value": q_weak.shape[0] * args.steps / (w_ms * 1e-3), "unit": "queries/s", "ms_per_step": w_ms / args.steps,
+                "kernel_ms": w_kern, "global_batch": int(q_weak.shape[0]), "batch_per_gpu": int(w["nq"])}
+
     # the same kernel with its visited filter off reads every neighbour row, like the CPU path does:
     # that run is the apples-to-apples HBM-bandwidth measurement against the reference-equivalent bytes
     nofilter_ms = []
     index.set_option("visited_filter_slots", 0)
     for i in range(4):
-        step_device()
+        searcher.search(q_dev, k)
         torch.cuda.synchronize()
         if i:
             nofilter_ms.append(index.last_kernel_ms())
     index.set_option("visited_filter_slots", args.filter_slots)
-    shard_ref_bytes = ref_bytes_per_query * (hi - lo)
-    t = torch.tensor([elapsed_ms, float(np.mean(kernel_ms)), shard_bytes, float(np.mean(nofilter_ms)), shard_ref_bytes],
-                     dtype=torch.float64, device=dev)
+    t = torch.tensor([shard_bytes, shard_ref_bytes, float(np.mean(nofilter_ms))], dtype=torch.float64, device=dev)
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         tsum = t.clone()
         dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        elapsed_ms, kern_ms, total_bytes = float(tmax[0]), float(tmax[1]), float(tsum[2])
-        nofilter, total_ref_bytes = float(tmax[3]), float(tsum[4])
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_bytes, total_ref_bytes, nofilter = float(tsum[0]), float(tsum[1]), float(t[2])
     else:
-        elapsed_ms, kern_ms, total_bytes = float(t[0]), float(t[1]), float(t[2])
-        nofilter, total_ref_bytes = float(t[3]), float(t[4])
-    qps = nq * args.steps / (elapsed_ms * 1e-3)
+        total_bytes, total_ref_bytes, nofilter = float(t[0]), float(t[1]), float(t[2])
 
-    # ---- end to end through the C ABI with host buffers (pinned): H2D + search + D2H per step ----
-    out_ids = torch.empty((hi - lo, k), dtype=torch.int64).pin_memory()
-    out_d = torch.empty((hi - lo, k), dtype=torch.float32).pin_memory()
-    q_shard = q_host[lo:hi]
+    # ---- end to end with HOST buffers, through the call a user makes ----
     cfg = index.search_parameters.buffer_config
+    if world == 1:
+        # svsb200_search (C ABI): pinned host queries in, host ids + distances out, H2D + kernels + D2H per step
+        q_host = torch.from_numpy(q_strong).pin_memory()
+        out_ids = torch.empty((nq, k), dtype=torch.int64).pin_memory()
+        out_d = torch.empty((nq, k), dtype=torch.float32).pin_memory()
 
-    def step_e2e():
-        _lib.check(lib.svsb200_search(index._h, q_shard.data_ptr(), 0, hi - lo, k, cfg.search_window_size,
-                                      cfg.search_buffer_capacity, 0, out_ids.data_ptr(), 8, out_d.data_ptr(), None))
+        def step_e2e():
+            _lib.check(lib.svsb200_search(index._h, q_host.data_ptr(), 0, nq, k, cfg.search_window_size,
+                                          cfg.search_buffer_capacity, 0, out_ids.data_ptr(), 8, out_d.data_ptr(), None))
+        e2e_path = "svsb200_search (C ABI): pinned host queries in, host ids + distances out"
+        h2d, d2h = int(nq * w["dim"] * 4), int(nq * k * 12)
+    else:
+        # every rank: H2D of its query slice, local search, NCCL all-gather of the rows; rank 0: D2H of the whole result
+        q_host = torch.from_numpy(np.ascontiguousarray(q_strong[lo:hi])).pin_memory()
+        q_stage = torch.empty((nq, w["dim"]), dtype=torch.float32, device=dev)
+        out_ids = torch.empty((nq, k), dtype=torch.int32).pin_memory()
+        out_d = torch.empty((nq, k), dtype=torch.float32).pin_memory()
 
+        def step_e2e():
+            q_stage[lo:hi].copy_(q_host, non_blocking=True)
+            ids, dd = searcher.search(q_stage, k)
+            if rank == 0:
+                out_ids.copy_(ids, non_blocking=True)
+                out_d.copy_(dd, non_blocking=True)
+            torch.cuda.synchronize()
+        e2e_path = ("per rank: pinned host query slice -> HBM, local search, NCCL all-gather of the result rows; rank 0: "
+                    "whole result -> pinned host; wall clock between barriers, max over ranks")
+        h2d, d2h = int(nq * w["dim"] * 4), int(nq * k * 8)
     for _ in range(3):
         step_e2e()
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
+    barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = nq * args.steps / float(te[0])
-    same = bool(np.array_equal(out_ids.numpy(), ids_all[lo:hi].cpu().numpy()))
+    same = bool(rank != 0 or np.array_equal(out_ids.numpy().astype(np.int64), ids_all.cpu().numpy().astype(np.int64)))
 
     if rank == 0:
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -376,7 +410,8 @@ def run_ours(args):
         ncu_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         if os.path.exists(ncu_path) and world == 1:
             ncu_traffic = json.load(open(ncu_path)).get(args.workload, {}).get("dram_bytes_per_launch")
-        # recall@10 on a sample against the exact top-k (svsb200_exhaustive_device: same distance code, ties by id)
+        # recall@10 on a sample against the exact top-k (svsb200_exhaustive_device: the search path's own distance code,
+        # ties by id; checked against the oracle in tests/test_gpu_parity.py::test_exhaustive_scan_is_exact_topk)
         sample = min(1000, nq)
         gt_ids = torch.empty((sample, k), dtype=torch.int64, device=dev)
         gt_d = torch.empty((sample, k), dtype=torch.float32, device=dev)
@@ -385,7 +420,7 @@ def run_ours(args):
         torch.cuda.synchronize()
         gt = gt_ids.cpu().numpy()
         got = ids_all[:sample].cpu().numpy()
-        recall = float(np.mean([len(set(got[i]) & set(gt[i])) for i in range(sample)])) / k
+        recall = float(np.mean([len(set(got[i].tolist()) & set(gt[i].tolist())) for i in range(sample)])) / k
 
         cpu = None
         if not args.no_cpu_baseline and world == 1:   # reported at N=1 only; `--impl reference` covers every N
@@ -393,55 +428,64 @@ def run_ours(args):
                 if lvq is not None:
                     raise NotImplementedError("LVQ is closed source in the reference: no reference arm for this workload")
                 threads = effective_cpus()
-                nb = w["nq"]   # the metric's batch (rank 0's block)
-                times, ref_ids, _, ref = time_reference(w, base, queries[:nb], graph, ep, 5, 1, threads)
+                nb = min(w["nq"], args.cpu_sample or w["nq"])   # the metric's batch (or a bounded sample of it)
+                reps = 5 if nb == w["nq"] and w["n"] * w["dim"] <= 2e8 else 1
+                times, ref_ids, ref_d, ref = time_reference(w, base, queries[:nb], graph, ep, reps, 1 if reps > 1 else 0,
+                                                            threads)
                 cpu_qps = nb / min(times)
                 ids_equal = bool(np.array_equal(ref_ids, ids_all[:nb].cpu().numpy().astype(np.uint64)))
+                d_equal = bool(np.array_equal(ref_d.view(np.uint32), d_all[:nb].cpu().numpy().view(np.uint32)))
                 cpu = {"value": nb * len(times) / sum(times), "best": cpu_qps, "unit": "queries/s", "cores": threads,
                        "kind": "reference",
-                       "sample": f"reference AVX-512 path (oracle/_ref, avx512={ref.avx512()}), full {nb}-query batch, "
-                                 f"1 warm-up + 5 timed searches on {threads} threads = the container's CPU quota "
-                                 f"(os.cpu_count()={os.cpu_count()})",
-                       "ids_identical_to_gpu": ids_equal}
+                       "sample": f"reference AVX-512 path (oracle/_ref, avx512={ref.avx512()}), first {nb} queries of the "
+                                 f"batch, {len(times)} timed searches on {threads} threads = the container's CPU quota "
+                                 f"(os.cpu_count()={os.cpu_count()}); {REF_PAGES}",
+                       "ids_identical_to_gpu": ids_equal, "distances_bit_identical_to_gpu": d_equal}
             except NotImplementedError:
                 from oracle.bindings import OracleLib   # own-spec LVQ-8: the CPU checker is the baseline ("port")
                 oidx = OracleLib().lvq8_index(lvq[0], w["dim"], lvq[1], graph, ep, w["metric"])
                 ns = 256
                 t0 = time.perf_counter()
-                o_ids, _ = oidx.search(queries[:ns], k, w["window"], w["window"])
+                o_ids, o_d = oidx.search(queries[:ns], k, w["window"], w["window"])
                 dt = time.perf_counter() - t0
                 cpu = {"value": ns / dt, "unit": "queries/s", "cores": 1, "kind": "port",
                        "sample": f"oracle/vamana_oracle.c LVQ-8 restatement, first {ns} queries, 1 thread (scalar)",
-                       "ids_identical_to_gpu": bool(np.array_equal(o_ids, ids_all[:ns].cpu().numpy().astype(np.uint64)))}
+                       "ids_identical_to_gpu": bool(np.array_equal(o_ids, ids_all[:ns].cpu().numpy().astype(np.uint64))),
+                       "distances_bit_identical_to_gpu": bool(np.array_equal(
+                           o_d.view(np.uint32), d_all[:ns].cpu().numpy().view(np.uint32)))}
             except Exception as e:   # noqa: BLE001
                 cpu = {"value": None, "unit": "queries/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
+        dram_frac = (ncu_traffic / (kern_ms * 1e-3) / 1e9 / peak) if ncu_traffic else None
         line = {
             "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if args.strong else "weak", "vs_baseline": None,
+            "scaling": "strong", "vs_baseline": None,
             "dtype": "f32" if lvq is None else "f32 (fused LVQ-8 decode)", "data": "synthetic",
-            "config": dict(workload_config(args.workload, w, graph), recall_at_10=round(recall, 4), global_batch=nq,
-                           batch_per_gpu=hi - lo,
-                           parallelism=f"replicas x{world}, query shards, NCCL all-gather of top-k"),
-            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(nq * w["dim"] * 4),
-                    "d2h_bytes_per_step": int(nq * k * 12), "matches_device_path": same,
-                    "path": "svsb200_search (C ABI) per rank on its own query block: pinned host queries in, host ids + "
-                            "distances out; max over ranks"},
+            "config": run_config(args.workload, w, graph, world, False),
+            "weak": weak,
+            "recall_at_10": round(recall, 4),
+            "parallelism": f"replicas x{world}: queries split with threads::balance, one NCCL all-gather of the top-k rows",
+            "kernel": {1: "vamana_search_fast_kernel", 0: "vamana_search_kernel"}[index.get_option("last_kernel")],
+            "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "matches_device_path": same, "path": e2e_path},
             "gpu_launches": int(launches),
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": ncu_traffic, "peak_source": peak_src, "kernel": "vamana_search_kernel", "kernel_ms": kern_ms,
+                "traffic": ncu_traffic, "peak_source": peak_src, "kernel_ms": kern_ms,
+                "frac_must_move": achieved / peak, "frac_survey_8d": ref_achieved / peak, "frac_dram_ncu": dram_frac,
+                "judged_on": "frac_must_move (the 0.60 target of BASELINE.json north_star)",
                 "algorithmic_bytes_per_query": bytes_per_query, "hops_per_query": float(hops.mean()),
                 "evals_per_query": float(evals.mean()), "rows_fetched_per_query": float(fetched.mean()),
-                "definition": "achieved = (adjacency rows + the base-vector rows that pass the kernel's exact visited "
-                              "filter + query + results) / kernel time, per GPU; i.e. the bytes this kernel must move",
-                "reference_equivalent": {
-                    "bytes_per_query": ref_bytes_per_query, "achieved": ref_achieved, "frac": ref_achieved / peak,
-                    "definition": "SURVEY.md 8(d): every neighbour evaluation of the CPU path (visited set off) charged "
-                                  "one row; above 1.0 because the filter skips the re-reads the CPU performs"},
+                "definition": "frac = frac_must_move = (adjacency rows + the base-vector rows that pass the kernel's exact "
+                              "visited filter + query + results) / kernel time / peak, per GPU: the bytes this kernel must "
+                              "move.  frac_survey_8d charges every neighbour evaluation of the CPU path (visited set off) "
+                              "one row (SURVEY.md 8d; above 1 because the filter skips the re-reads the CPU performs).  "
+                              "frac_dram_ncu = ncu dram__bytes per launch (profiles/ncu_traffic.json) / kernel time / peak.",
+                "reference_equivalent": {"bytes_per_query": ref_bytes_per_query, "achieved": ref_achieved,
+                                         "frac": ref_achieved / peak},
                 "filter_off": {
                     "kernel_ms": nofilter, "achieved": nofilter_achieved, "frac": nofilter_achieved / peak,
-                    "definition": "same kernel, visited filter disabled: reads every row the reference reads; "
+                    "definition": "generic kernel, visited filter disabled: reads every row the reference reads; "
                                   "reference-equivalent bytes / its own kernel time"}},
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
@@ -543,9 +587,11 @@ def main():
     ap.add_argument("--filter-slots", dest="filter_slots", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svsb200_set_option)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--strong", action="store_true",
-                    help="keep the global batch at the single-GPU size and split it over the GPUs (default: weak "
-                         "scaling, every GPU keeps the metric's 10k-query batch)")
+    ap.add_argument("--weak", action="store_true",
+                    help="reference arm only: label the line as the weak-scaling batch (our arm reports the strong "
+                         "result as `value` and the weak one under `weak` in the same line)")
+    ap.add_argument("--cpu-sample", dest="cpu_sample", type=int, default=0,
+                    help="cpu_baseline: time only the first N queries of the batch (bounded sample for big workloads)")
     args = ap.parse_args()
     if WORKLOADS[args.workload].get("sharded"):
         run_sharded(args)

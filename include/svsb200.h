@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SVSB200_VERSION 100
+#define SVSB200_VERSION 200
 
 /* Element types: svs::DataType float32 / float16 / int8 / uint8 (lib/datatype.h). */
 enum { SVSB200_F32 = 0, SVSB200_F16 = 1, SVSB200_I8 = 2, SVSB200_U8 = 3 };
@@ -64,6 +64,16 @@ int svsb200_index_create(
     const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric,
     int storage, const float* aux, int device, svsb200_index** out);
 
+/* The same index replicated on several GPUs of this process (SURVEY.md 8e mode A, the multi-device form of
+ * the reference's `num_threads`): replica 0 is uploaded from the host arrays, the others are copied device to
+ * device.  svsb200_search on such an index splits every batch with threads::balance
+ * (lib/threads/types.h:311-329), one contiguous slice per device, and the slices' results land in disjoint
+ * rows of the caller's arrays -- no collective. */
+int svsb200_index_create_multi(
+    const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes,
+    const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric,
+    int storage, const float* aux, const int* devices, size_t ndevices, svsb200_index** out);
+
 int svsb200_index_destroy(svsb200_index* index);
 
 /* Introspection used by the host-side mirror (size()/dimensions()/get_graph_max_degree,
@@ -72,7 +82,8 @@ size_t svsb200_index_size(const svsb200_index* index);
 size_t svsb200_index_dimensions(const svsb200_index* index);
 size_t svsb200_index_max_degree(const svsb200_index* index);
 size_t svsb200_index_device_bytes(const svsb200_index* index);
-int svsb200_index_device(const svsb200_index* index);
+int svsb200_index_device(const svsb200_index* index);         /* first replica's device */
+size_t svsb200_index_num_devices(const svsb200_index* index);
 
 /* Replaces: VamanaIndex::search(QueryResultView<I>, queries, VamanaSearchParameters, cancel)
  *           (include/svs/index/vamana/index.h:564-611) for a whole batch.
@@ -92,13 +103,26 @@ int svsb200_search(
     size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists,
     void* stream);
 
+/* svsb200_search with the reference's cancellation predicate (`const lib::DefaultPredicate& cancel`,
+ * index/vamana/index.h:568): while the batch runs, the calling thread polls `cancel(cancel_arg)`; once it
+ * returns non-zero a device flag is raised that every search warp polls per query and per expanded node
+ * (extensions.h:579, greedy_search.h:155) and the call returns as soon as the kernels have drained.  As in
+ * the reference, the result rows of a cancelled call are unspecified. */
+int svsb200_search_cancellable(
+    svsb200_index* index, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+    size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists,
+    void* stream, int (*cancel)(void*), void* cancel_arg);
+
+/* Threading: concurrent svsb200_search* calls on one index from several host threads are allowed (as the
+ * reference allows concurrent searches with external scratch, index/vamana/index.h:455-470,512-526): every
+ * call checks out its own stream + scratch buffers (svsb200_get_option "streams" reports how many exist). */
+
 /* Same search with every buffer already resident in HBM on the index's device and no
  * synchronisation: enqueues on `stream` and returns (bench.py's device-resident `value`,
- * multi-GPU pipelines that feed NCCL directly).  An index owns one set of device scratch
- * buffers (prepared queries, work counter): searches enqueued on the same index must be
- * ordered on one stream (or separated by a synchronisation); use one index handle per
- * concurrent stream -- the analogue of the reference's per-thread scratch space
- * (index/vamana/index.h:455-470). */
+ * multi-GPU pipelines that feed NCCL directly).  The index keeps one set of scratch buffers
+ * (prepared queries, work counter) per caller stream -- the analogue of the reference's
+ * per-thread scratch space (index/vamana/index.h:455-470) -- so different streams may search
+ * concurrently; single-device indexes only. */
 int svsb200_search_device(
     svsb200_index* index, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
     size_t capacity, int use_visited_set, void* d_out_ids, int id_bytes, float* d_out_dists,
@@ -130,6 +154,17 @@ int svsb200_set_option(svsb200_index* index, const char* name, long value);
  * one-warp-per-CTA kernel, 0 = the generic kernel that covers every other configuration), and
  * "generic_kernel" (set to 1 to force the generic kernel; results are identical). */
 int svsb200_get_option(svsb200_index* index, const char* name, long* value);
+
+/* Mode B of SURVEY.md §8e inside one process: `shards[s]` are single-device indexes over disjoint,
+ * contiguous id ranges of one dataset, each with its own graph and entry point and its id range's first id
+ * set with svsb200_set_id_offset.  Every query is searched on every shard; the per-shard top-k rows are
+ * gathered on shard 0's device -- written there directly by the shards' search kernels over NVLink when
+ * peer access exists, by peer copies otherwise -- and merged G*k -> k with the reference's TotalOrder
+ * (distance, then id; lib/neighbor.h:143-155).  Host buffers in, host buffers out; blocking. */
+int svsb200_set_id_offset(svsb200_index* index, uint64_t offset);
+int svsb200_search_sharded(
+    svsb200_index* const* shards, size_t nshards, const void* queries, int qdtype, size_t nq, size_t k,
+    size_t window, size_t capacity, uint64_t* out_ids, float* out_dists);
 
 /* Mode B of SURVEY.md §8e -- merge per-shard top-k lists (after an NCCL all-gather) into a
  * global top-k with the reference's TotalOrder (distance, then id; lib/neighbor.h:143-155).

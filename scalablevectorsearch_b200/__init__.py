@@ -4,9 +4,9 @@ Only the hot path of SURVEY.md §8 lives here: ``csrc/`` (CUDA kernels + C ABI -
 the host-side mirror of the reference's search interface (:mod:`.vamana`), and the file formats
 around it (:mod:`.io`).
 """
-from .vamana import (DataType, DistanceType, GraphLoader, SearchBufferConfig, Vamana, VamanaSearchParameters,
-                     VectorDataLoader, lvq8_compress)
+from .vamana import (DataType, DistanceType, GraphLoader, SearchBufferConfig, ShardedVamana, Vamana,
+                     VamanaSearchParameters, VectorDataLoader, lvq8_compress)
 from ._lib import Svsb200Error
 
 __all__ = ["DataType", "DistanceType", "GraphLoader", "SearchBufferConfig", "Vamana", "VamanaSearchParameters",
-           "VectorDataLoader", "Svsb200Error", "lvq8_compress"]
+           "VectorDataLoader", "Svsb200Error", "lvq8_compress", "ShardedVamana"]

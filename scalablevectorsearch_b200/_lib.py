@@ -20,9 +20,13 @@ SYMBOLS = [
     "svsb200_index_device", "svsb200_search", "svsb200_search_device", "svsb200_set_counting",
     "svsb200_get_counters", "svsb200_get_fetched", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option", "svsb200_get_option",
     "svsb200_merge_topk_device", "svsb200_exhaustive_device", "svsb200_lvq8_row_stride", "svsb200_lvq8_compress",
+    "svsb200_index_create_multi", "svsb200_index_num_devices", "svsb200_search_cancellable", "svsb200_set_id_offset",
+    "svsb200_search_sharded",
 ]
 
 _lib = None
+#: the cancellation predicate of svsb200_search_cancellable: int (*)(void*)
+CANCEL_FN = C.CFUNCTYPE(C.c_int, C.c_void_p)
 
 
 class Svsb200Error(RuntimeError):
@@ -60,6 +64,12 @@ def lib() -> C.CDLL:
     l.svsb200_lvq8_row_stride.restype, l.svsb200_lvq8_row_stride.argtypes = sz, [sz]
     l.svsb200_lvq8_compress.argtypes = [vp, sz, sz, vp, vp, i32]
     l.svsb200_exhaustive_device.argtypes = [vp, vp, i32, sz, sz, vp, vp, vp]
+    l.svsb200_index_create_multi.argtypes = [vp, i32, sz, sz, sz, vp, sz, u32, i32, i32, vp, C.POINTER(i32), sz,
+                                             C.POINTER(vp)]
+    l.svsb200_index_num_devices.restype, l.svsb200_index_num_devices.argtypes = sz, [vp]
+    l.svsb200_search_cancellable.argtypes = [vp, vp, i32, sz, sz, sz, sz, i32, vp, i32, vp, vp, CANCEL_FN, vp]
+    l.svsb200_set_id_offset.argtypes = [vp, C.c_uint64]
+    l.svsb200_search_sharded.argtypes = [C.POINTER(vp), sz, vp, i32, sz, sz, sz, sz, vp, vp]
     _lib = l
     return l
 

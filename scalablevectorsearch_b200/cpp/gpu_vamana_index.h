@@ -34,6 +34,7 @@
 
 #include <memory>
 #include <type_traits>
+#include <vector>
 
 namespace svsb200 {
 
@@ -71,6 +72,12 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
     /// Take over an assembled (or freshly built) CPU index and mirror its graph and vectors
     /// into the HBM of `device`.  The host copies stay alive for the non-search members.
     explicit GpuVamanaIndex(base_type&& cpu, int device = 0)
+        : GpuVamanaIndex(std::move(cpu), std::vector<int>{device}) {}
+
+    /// The same, replicated on several GPUs: every batch is split with the reference's own
+    /// `threads::balance` (lib/threads/types.h:311-329), one slice per device -- the multi-device form of
+    /// the thread-pool partition in index.h:571-574.
+    GpuVamanaIndex(base_type&& cpu, const std::vector<int>& devices)
         : base_type(std::move(cpu)) {
         this->experimental_escape_hatch([&](const auto& graph,
                                             const auto& data,
@@ -84,7 +91,7 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
             if constexpr (svs::quantization::scalar::IsSQData<Data>) {
                 using E = typename Data::element_type;
                 const float aux[2] = {data.get_scale(), data.get_bias()};
-                detail::check(svsb200_index_create(
+                detail::check(svsb200_index_create_multi(
                     data.get_datum(0).data(),
                     detail::DTypeCode<E>::value,
                     data.size(),
@@ -96,12 +103,13 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
                     detail::MetricCode<Dist>::value,
                     SVSB200_SQ,
                     aux,
-                    device,
+                    devices.data(),
+                    devices.size(),
                     &raw
                 ));
             } else {
                 using E = std::remove_const_t<typename Data::element_type>;
-                detail::check(svsb200_index_create(
+                detail::check(svsb200_index_create_multi(
                     data.data(),
                     detail::DTypeCode<E>::value,
                     data.size(),
@@ -113,7 +121,8 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
                     detail::MetricCode<Dist>::value,
                     SVSB200_PLAIN,
                     nullptr,
-                    device,
+                    devices.data(),
+                    devices.size(),
                     &raw
                 ));
             }
@@ -141,16 +150,17 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
                 this->dimensions()
             );
         }
-        // The predicate cannot be polled from the device: honour it at batch granularity
-        // (the reference polls per query and per hop, greedy_search.h:155, extensions.h:579).
-        if (cancel()) {
-            return;
-        }
+        // The predicate is polled by this thread while the batch runs; once it fires, a device flag stops
+        // every search warp at its next query / hop boundary (the reference polls at greedy_search.h:155
+        // and extensions.h:579).
         const size_t nq = queries.size();
         if (nq == 0) {
             return;
         }
-        detail::check(svsb200_search(
+        auto trampoline = [](void* arg) -> int {
+            return (*static_cast<const svs::lib::DefaultPredicate*>(arg))() ? 1 : 0;
+        };
+        detail::check(svsb200_search_cancellable(
             handle_.get(),
             queries.get_datum(0).data(),
             detail::DTypeCode<Q>::value,
@@ -162,9 +172,14 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
             &result.index(0, 0),
             static_cast<int>(sizeof(I)),
             &result.distance(0, 0),
-            nullptr
+            nullptr,
+            +trampoline,
+            const_cast<void*>(static_cast<const void*>(&cancel))
         ));
     }
+
+    /// Devices holding a replica ("threadpool -> CUDA streams": every calling thread gets its own stream).
+    size_t num_devices() const { return svsb200_index_num_devices(handle_.get()); }
 
     std::string name() const { return "GpuVamanaIndex (libsvsb200, sm_100a)"; }
     svsb200_index* native_handle() const { return handle_.get(); }
@@ -178,6 +193,9 @@ GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&, int)
     -> GpuVamanaIndex<Graph, Data, Dist>;
 template <typename Graph, typename Data, typename Dist>
 GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&)
+    -> GpuVamanaIndex<Graph, Data, Dist>;
+template <typename Graph, typename Data, typename Dist>
+GpuVamanaIndex(svs::index::vamana::VamanaIndex<Graph, Data, Dist>&&, const std::vector<int>&)
     -> GpuVamanaIndex<Graph, Data, Dist>;
 
 /// Type-erase a GpuVamanaIndex into the reference's orchestrator object.

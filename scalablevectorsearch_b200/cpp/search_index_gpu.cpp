@@ -27,7 +27,7 @@ void run(
     const std::filesystem::path& graph,
     const std::filesystem::path& data,
     const std::string& prefix,
-    int device
+    const std::vector<int>& devices
 ) {
     auto cpu = svs::index::vamana::auto_assemble(
         config,
@@ -36,7 +36,7 @@ void run(
         Dist{},
         threads
     );
-    auto index = svsb200::make_gpu_vamana<svs::lib::Types<Eq>>(svsb200::GpuVamanaIndex{std::move(cpu), device});
+    auto index = svsb200::make_gpu_vamana<svs::lib::Types<Eq>>(svsb200::GpuVamanaIndex{std::move(cpu), devices});
     index.set_search_parameters(index.get_search_parameters().buffer_config({window}));
     const auto queries = svs::load_data<Eq>(query_file);
     auto tic = svs::lib::now();
@@ -70,7 +70,7 @@ int main(int argc, char** argv) {
             stderr,
             "usage: %s <query type: float|float16|int8|uint8> <data type> <query file> <search window> "
             "<neighbors> <threads> <config dir> <graph dir> <data dir> <result prefix> <L2|MIP|Cosine> "
-            "[device]\n",
+            "[device[,device...]]   (several devices: one replica each, the batch is split over them)\n",
             argv[0]
         );
         return 2;
@@ -80,9 +80,14 @@ int main(int argc, char** argv) {
         const size_t window = std::stoul(argv[4]), k = std::stoul(argv[5]), threads = std::stoul(argv[6]);
         const std::filesystem::path config = argv[7], graph = argv[8], data = argv[9];
         const std::string prefix = argv[10], dist = argv[11];
-        const int device = argc == 13 ? std::stoi(argv[12]) : 0;
+        std::vector<int> devices;
+        for (std::string rest = argc == 13 ? argv[12] : "0"; !rest.empty();) {
+            const size_t comma = rest.find(',');
+            devices.push_back(std::stoi(rest.substr(0, comma)));
+            rest = comma == std::string::npos ? "" : rest.substr(comma + 1);
+        }
         auto go = [&]<typename Eq, typename Edb>() {
-            by_distance<Eq, Edb>(dist, qfile, window, k, threads, config, graph, data, prefix, device);
+            by_distance<Eq, Edb>(dist, qfile, window, k, threads, config, graph, data, prefix, devices);
         };
         if (qt == "float" && dt == "float") {
             go.template operator()<float, float>();

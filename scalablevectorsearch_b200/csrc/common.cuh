@@ -61,6 +61,7 @@ struct SearchParams {
     // outputs
     void* out_ids;
     int id_bytes;
+    uint64_t id_offset;        // added to every valid 64-bit output id (this index is a shard of a larger one)
     float* out_dists;
     // bookkeeping
     unsigned int* work_counter;  // dynamic query scheduler

@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             const float dist = valid ? __fmul_rn(__uint_as_float(e.x), ksign) : (p.greater ? -INFINITY : INFINITY);
             const size_t o = size_t(q) * p.k + j;
             if (p.id_bytes == 8)
-                reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) : ~uint64_t(0);
+                reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) + p.id_offset : ~uint64_t(0);
             else
                 reinterpret_cast<uint32_t*>(p.out_ids)[o] = id;
             p.out_dists[o] = dist;

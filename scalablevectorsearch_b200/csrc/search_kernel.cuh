@@ -608,6 +608,8 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
         if (lane == 0) q = atomicAdd(p.work_counter, 1u);
         q = __shfl_sync(FULL, q, 0);
         if (q >= p.nq) break;
+        // cancellation between queries (extensions.h:579)
+        if (p.cancel && *reinterpret_cast<const volatile int*>(p.cancel)) break;
 
         // ---- stage the prepared query (maybe_fix_argument already applied) ----
         if constexpr (kInt) {
@@ -644,6 +646,8 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
 
         // ---- main loop: while (!buffer.done()) (greedy_search.h:153) ----
         for (;;) {
+            // cancellation inside a search (greedy_search.h:155)
+            if (p.cancel && *reinterpret_cast<const volatile int*>(p.cancel)) break;
             uint32_t deg = 0;
             if constexpr (EXH) {
                 if (scan_base >= p.n) break;
@@ -836,7 +840,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
             const float dist = valid ? __fmul_rn(bkey[j], ksign) : (p.greater ? -INFINITY : INFINITY);
             const size_t o = size_t(q) * p.k + j;
             if (p.id_bytes == 8)
-                reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) : ~uint64_t(0);
+                reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) + p.id_offset : ~uint64_t(0);
             else
                 reinterpret_cast<uint32_t*>(p.out_ids)[o] = id;
             p.out_dists[o] = dist;

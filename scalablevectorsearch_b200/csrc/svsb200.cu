@@ -1,14 +1,27 @@
-// svsb200.cu -- C ABI (include/svsb200.h) of the B200 Vamana search library: index upload,
-// query preparation (the device-side maybe_fix_argument), launch plumbing, result gather.
+// svsb200.cu -- C ABI (include/svsb200.h) of the B200 Vamana search library: index upload to one or
+// several GPUs, query preparation (the device-side maybe_fix_argument), launch plumbing, result gather.
 //
-// No CPU fallback lives here: every entry point either runs CUDA kernels on an sm_100
-// device or fails with an error.
+// Host-side structure (the reference's thread pool -> CUDA streams, index/vamana/index.h:455-470,564-611):
+//   * an index owns one Replica per device (graph + vectors in that device's HBM);
+//   * every search call checks a Scratch (stream + prepared-query buffers + work counter + cancel flag) out
+//     of the replica's pool, so concurrent host threads search concurrently on their own streams;
+//   * a multi-replica index splits a batch with threads::balance (lib/threads/types.h:311-329), one slice per
+//     device, results landing in disjoint rows of the caller's arrays (SURVEY.md 8e mode A);
+//   * svsb200_search_sharded runs every query on every shard index and merges G*k -> k on one device with
+//     the reference's TotalOrder (mode B); with NVLink peer access the shards' search kernels write their
+//     rows straight into the merging device's buffer.
+//
+// No CPU fallback lives here: every entry point either runs CUDA kernels on an sm_100 device or fails.
 #include "common.cuh"
 
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <map>
+#include <memory>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 namespace svsb200 {
@@ -37,7 +50,7 @@ template <typename T> struct DeviceBuffer {
     size_t count = 0;
     cudaError_t ensure(size_t n) {
         if (n <= count) return cudaSuccess;
-        if (ptr) cudaFree(ptr);
+        if (ptr) cudaFree(ptr);   // (synchronises the device: safe against work still using the old block)
         ptr = nullptr;
         count = 0;
         cudaError_t err = cudaMalloc(&ptr, n * sizeof(T));
@@ -51,39 +64,142 @@ template <typename T> struct DeviceBuffer {
     }
 };
 
+// Everything one in-flight search needs on one device: the analogue of the reference's per-thread scratch
+// space (index/vamana/index.h:455-470).
+struct Scratch {
+    int device = 0;
+    cudaStream_t stream = nullptr;   // own non-blocking stream (blocking API) or the caller's (device API)
+    cudaStream_t ctl = nullptr;      // side stream that raises the cancel flag while `stream` is busy
+    bool owns_stream = false;
+    DeviceBuffer<unsigned char> q_raw, q_codes, ids;
+    DeviceBuffer<float> q_f32, q_aux, dists;
+    DeviceBuffer<uint32_t> hops, evals, fetched;
+    DeviceBuffer<uint64_t> gather_ids, merged_ids;     // sharded search (on the merging device)
+    DeviceBuffer<float> gather_dists, merged_dists;
+    unsigned int* d_counter = nullptr;
+    int* d_cancel = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
+    bool timed = false;
+    size_t counted_nq = 0;
+    int last_kernel = 0;
+    ~Scratch() {
+        cudaSetDevice(device);
+        q_raw.release(); q_codes.release(); ids.release(); q_f32.release(); q_aux.release(); dists.release();
+        hops.release(); evals.release(); fetched.release();
+        gather_ids.release(); merged_ids.release(); gather_dists.release(); merged_dists.release();
+        if (d_counter) cudaFree(d_counter);
+        if (d_cancel) cudaFree(d_cancel);
+        if (ev_start) cudaEventDestroy(ev_start);
+        if (ev_stop) cudaEventDestroy(ev_stop);
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (ctl) cudaStreamDestroy(ctl);
+        if (owns_stream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+// One copy of the index in one device's HBM.
+struct Replica {
+    int device = 0;
+    int sm_count = 0;
+    void* d_vectors = nullptr;
+    uint32_t* d_graph = nullptr;
+    uint16_t* d_ref_degree = nullptr;
+    float* d_mean = nullptr;          // LVQ-8: dataset mean
+    std::mutex mu;
+    std::vector<Scratch*> idle;                      // pool for the blocking API
+    std::map<cudaStream_t, Scratch*> by_stream;      // one per caller stream for the enqueue-only API
+    std::vector<std::unique_ptr<Scratch>> all;
+    ~Replica() {
+        cudaSetDevice(device);
+        all.clear();
+        if (d_vectors) cudaFree(d_vectors);
+        if (d_graph) cudaFree(d_graph);
+        if (d_ref_degree) cudaFree(d_ref_degree);
+        if (d_mean) cudaFree(d_mean);
+    }
+};
+
 }  // namespace svsb200
 
 using namespace svsb200;
 
 struct svsb200_index {
-    int device = 0;
-    int sm_count = 0;
     int dtype = 0, metric = 0, storage = 0;
     size_t n = 0, dim = 0, max_degree = 0;
     uint32_t row_stride = 0, gstride = 0, entry_point = 0;
     float scale = 1.f, bias = 0.f;
-    void* d_vectors = nullptr;
-    uint32_t* d_graph = nullptr;
-    uint16_t* d_ref_degree = nullptr;
-    float* d_mean = nullptr;          // LVQ-8: dataset mean
     uint32_t lvq_const_offset = 0;
-    size_t device_bytes = 0;
-    // scratch, grown on demand
-    DeviceBuffer<unsigned char> q_raw, q_codes, ids;
-    DeviceBuffer<float> q_f32, q_aux, dists;
-    DeviceBuffer<uint32_t> hops, evals, fetched;
-    unsigned int* d_counter = nullptr;
+    size_t device_bytes = 0;          // per replica
+    uint64_t id_offset = 0;           // added to every 64-bit output id (shard of a larger index)
+    std::vector<std::unique_ptr<Replica>> reps;
     int counting = 0;
-    size_t counted_nq = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
-    bool timed = false;
     // options
     long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
-    long generic_kernel = 0;   // 1: force the generic (round-1) kernel instead of the lean one
-    int last_kernel = 0;       // 1 = lean kernel, 0 = generic kernel (introspection for tests)
-    std::mutex mutex;
+    long generic_kernel = 0;          // 1: force the generic (round-1) kernel instead of the lean one
+    std::mutex mu;
+    Scratch* last = nullptr;          // scratch of the most recent search: counters, kernel time, kernel kind
 };
+
+namespace svsb200 {
+
+static Scratch* new_scratch(Replica* rep, cudaStream_t caller_stream, std::string* err) {
+    auto sc = std::make_unique<Scratch>();
+    sc->device = rep->device;
+    cudaError_t e = cudaSuccess;
+    if (caller_stream) {
+        sc->stream = caller_stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&sc->stream, cudaStreamNonBlocking);
+        sc->owns_stream = true;
+    }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&sc->ctl, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_counter, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_cancel, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(sc->d_cancel, 0, sizeof(int));
+    if (e == cudaSuccess) e = cudaEventCreate(&sc->ev_start);
+    if (e == cudaSuccess) e = cudaEventCreate(&sc->ev_stop);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sc->ev_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        *err = std::string("scratch allocation: ") + cudaGetErrorString(e);
+        return nullptr;
+    }
+    Scratch* raw = sc.get();
+    rep->all.push_back(std::move(sc));
+    return raw;
+}
+
+// Blocking API: any idle scratch of the replica (a new one if all are busy -- one per concurrent caller).
+static Scratch* acquire(Replica* rep, std::string* err) {
+    std::lock_guard<std::mutex> lock(rep->mu);
+    if (!rep->idle.empty()) {
+        Scratch* sc = rep->idle.back();
+        rep->idle.pop_back();
+        return sc;
+    }
+    return new_scratch(rep, nullptr, err);
+}
+static void release(Replica* rep, Scratch* sc) {
+    std::lock_guard<std::mutex> lock(rep->mu);
+    rep->idle.push_back(sc);
+}
+// Enqueue-only API: the scratch bound to the caller's stream (work on one stream is ordered, so it is reusable).
+static Scratch* scratch_for_stream(Replica* rep, cudaStream_t stream, std::string* err) {
+    std::lock_guard<std::mutex> lock(rep->mu);
+    auto it = rep->by_stream.find(stream);
+    if (it != rep->by_stream.end()) return it->second;
+    Scratch* sc = new_scratch(rep, stream, err);
+    if (sc) rep->by_stream[stream] = sc;
+    return sc;
+}
+
+// threads::balance (lib/threads/types.h:311-329): contiguous ranges whose sizes differ by at most one.
+static void balance(size_t n, size_t parts, size_t i, size_t* lo, size_t* hi) {
+    const size_t base = n / parts, rem = n % parts;
+    *lo = i * base + (i < rem ? i : rem);
+    *hi = *lo + base + (i < rem ? 1 : 0);
+}
+
+}  // namespace svsb200
 
 namespace svsb200 {
 
@@ -408,12 +524,77 @@ int svsb200_device_sm(int device, int* sm) {
     return 0;
 }
 
-int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes,
-                         const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric, int storage,
-                         const float* aux, int device, svsb200_index** out) {
+// Uploads one replica from the host arrays.
+static int upload_replica(svsb200_index* ix, Replica* rep, const void* vectors, size_t src_stride, size_t row_bytes,
+                          const uint32_t* graph_rows, size_t graph_row_len, const float* aux) {
+    const size_t n = ix->n;
+    CUDA_TRY(cudaSetDevice(rep->device));
+    const size_t vbytes = n * size_t(ix->row_stride);
+    const size_t gbytes = n * size_t(ix->gstride) * sizeof(uint32_t);
+    CUDA_TRY(cudaMalloc(&rep->d_vectors, vbytes));
+    CUDA_TRY(cudaMalloc(&rep->d_graph, gbytes));
+    CUDA_TRY(cudaMalloc(&rep->d_ref_degree, n * sizeof(uint16_t)));
+    ix->device_bytes = vbytes + gbytes + n * sizeof(uint16_t);
+    CUDA_TRY(cudaMemset(rep->d_vectors, 0, vbytes));
+    CUDA_TRY(cudaMemcpy2D(rep->d_vectors, ix->row_stride, vectors, src_stride, row_bytes, n, cudaMemcpyHostToDevice));
+    {
+        uint32_t* d_src = nullptr;
+        int* d_bad = nullptr;
+        const size_t sbytes = n * graph_row_len * sizeof(uint32_t);
+        CUDA_TRY(cudaMalloc(&d_src, sbytes));
+        cudaError_t err = cudaMalloc(&d_bad, sizeof(int));
+        if (err == cudaSuccess) err = cudaMemset(d_bad, 0, sizeof(int));
+        if (err == cudaSuccess) err = cudaMemcpy(d_src, graph_rows, sbytes, cudaMemcpyHostToDevice);
+        int bad = 0;
+        if (err == cudaSuccess) {
+            const int warps = 8;
+            repack_graph_kernel<<<unsigned((n + warps - 1) / warps), warps * 32>>>(d_src, graph_row_len, uint32_t(n),
+                                                                                  rep->d_graph, ix->gstride,
+                                                                                  rep->d_ref_degree, d_bad);
+            count_launch();
+            err = cudaGetLastError();
+        }
+        if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
+        cudaFree(d_src);
+        if (d_bad) cudaFree(d_bad);
+        CUDA_TRY(err);
+        if (bad)
+            return fail(bad == 1 ? "svsb200_index_create: adjacency row with degree > max_degree"
+                                 : "svsb200_index_create: neighbour id out of range");
+    }
+    if (ix->storage == SVSB200_LVQ8) {
+        CUDA_TRY(cudaMalloc(&rep->d_mean, ix->dim * sizeof(float)));
+        CUDA_TRY(cudaMemcpy(rep->d_mean, aux, ix->dim * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    return 0;
+}
+
+// Copies an uploaded replica device to device (NVLink when peer access exists).
+static int clone_replica(svsb200_index* ix, const Replica* src, Replica* dst) {
+    const size_t n = ix->n;
+    CUDA_TRY(cudaSetDevice(dst->device));
+    const size_t vbytes = n * size_t(ix->row_stride);
+    const size_t gbytes = n * size_t(ix->gstride) * sizeof(uint32_t);
+    CUDA_TRY(cudaMalloc(&dst->d_vectors, vbytes));
+    CUDA_TRY(cudaMalloc(&dst->d_graph, gbytes));
+    CUDA_TRY(cudaMalloc(&dst->d_ref_degree, n * sizeof(uint16_t)));
+    CUDA_TRY(cudaMemcpyPeer(dst->d_vectors, dst->device, src->d_vectors, src->device, vbytes));
+    CUDA_TRY(cudaMemcpyPeer(dst->d_graph, dst->device, src->d_graph, src->device, gbytes));
+    CUDA_TRY(cudaMemcpyPeer(dst->d_ref_degree, dst->device, src->d_ref_degree, src->device, n * sizeof(uint16_t)));
+    if (src->d_mean) {
+        CUDA_TRY(cudaMalloc(&dst->d_mean, ix->dim * sizeof(float)));
+        CUDA_TRY(cudaMemcpyPeer(dst->d_mean, dst->device, src->d_mean, src->device, ix->dim * sizeof(float)));
+    }
+    return 0;
+}
+
+int svsb200_index_create_multi(const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes,
+                               const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric,
+                               int storage, const float* aux, const int* devices, size_t ndevices, svsb200_index** out) {
     if (!out) return fail("svsb200_index_create: out is NULL");
     *out = nullptr;
     if (!vectors || !graph_rows) return fail("svsb200_index_create: NULL input");
+    if (!devices || ndevices == 0) return fail("svsb200_index_create: empty device list");
     if (dtype < SVSB200_F32 || dtype > SVSB200_U8) return fail("svsb200_index_create: bad dtype");
     if (metric < SVSB200_L2 || metric > SVSB200_COSINE) return fail("svsb200_index_create: bad metric");
     if (n == 0 || dim == 0) return fail("svsb200_index_create: empty dataset");
@@ -432,18 +613,10 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
     } else if (storage != SVSB200_PLAIN) {
         return fail("svsb200_index_create: unsupported storage kind");
     }
-    int ndev = svsb200_device_count();
+    const int ndev = svsb200_device_count();
     if (ndev == 0) return fail("svsb200_index_create: no CUDA device (there is no CPU fallback)");
-    if (device < 0 || device >= ndev) return fail("svsb200_index_create: bad device ordinal");
-    CUDA_TRY(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10 || prop.minor != 0)
-        return fail("svsb200_index_create: device is not sm_100 (this binary holds sm_100a code only)");
 
-    auto* ix = new svsb200_index();
-    ix->device = device;
-    ix->sm_count = prop.multiProcessorCount;
+    std::unique_ptr<svsb200_index> ix(new svsb200_index());
     ix->dtype = dtype;
     ix->metric = metric;
     ix->storage = storage;
@@ -466,88 +639,36 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
     // the lean kernel, no per-lane bounds checks); wider rows stay 16-byte aligned only
     ix->gstride = uint32_t(round_up(ix->max_degree, ix->max_degree <= 32u * kFastMaxGW ? 32 : 4));
 
-    auto cleanup = [&](int rc) {
-        svsb200_index_destroy(ix);
-        return rc;
-    };
-#define CUDA_TRY_IX(expr)                                                                      \
-    do {                                                                                       \
-        cudaError_t err__ = (expr);                                                            \
-        if (err__ != cudaSuccess) {                                                            \
-            fail(std::string(#expr) + ": " + cudaGetErrorString(err__));                       \
-            return cleanup(1);                                                                 \
-        }                                                                                      \
-    } while (0)
-
-    const size_t vbytes = n * size_t(ix->row_stride);
-    const size_t gbytes = n * size_t(ix->gstride) * sizeof(uint32_t);
-    CUDA_TRY_IX(cudaMalloc(&ix->d_vectors, vbytes));
-    CUDA_TRY_IX(cudaMalloc(&ix->d_graph, gbytes));
-    CUDA_TRY_IX(cudaMalloc(&ix->d_ref_degree, n * sizeof(uint16_t)));
-    ix->device_bytes = vbytes + gbytes + n * sizeof(uint16_t);
-    CUDA_TRY_IX(cudaMemset(ix->d_vectors, 0, vbytes));
-    CUDA_TRY_IX(cudaMemcpy2D(ix->d_vectors, ix->row_stride, vectors, src_stride, row_bytes, n, cudaMemcpyHostToDevice));
-    {
-        uint32_t* d_src = nullptr;
-        int* d_bad = nullptr;
-        const size_t sbytes = n * graph_row_len * sizeof(uint32_t);
-        CUDA_TRY_IX(cudaMalloc(&d_src, sbytes));
-        cudaError_t err = cudaMalloc(&d_bad, sizeof(int));
-        if (err == cudaSuccess) err = cudaMemset(d_bad, 0, sizeof(int));
-        if (err == cudaSuccess) err = cudaMemcpy(d_src, graph_rows, sbytes, cudaMemcpyHostToDevice);
-        int bad = 0;
-        if (err == cudaSuccess) {
-            const int warps = 8;
-            repack_graph_kernel<<<unsigned((n + warps - 1) / warps), warps * 32>>>(d_src, graph_row_len, uint32_t(n),
-                                                                                  ix->d_graph, ix->gstride,
-                                                                                  ix->d_ref_degree, d_bad);
-            count_launch();
-            err = cudaGetLastError();
-        }
-        if (err == cudaSuccess) err = cudaMemcpy(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost);
-        cudaFree(d_src);
-        if (d_bad) cudaFree(d_bad);
-        CUDA_TRY_IX(err);
-        if (bad) {
-            fail(bad == 1 ? "svsb200_index_create: adjacency row with degree > max_degree"
-                          : "svsb200_index_create: neighbour id out of range");
-            return cleanup(1);
-        }
+    for (size_t r = 0; r < ndevices; ++r) {
+        const int device = devices[r];
+        if (device < 0 || device >= ndev) return fail("svsb200_index_create: bad device ordinal");
+        for (size_t j = 0; j < r; ++j)
+            if (devices[j] == device) return fail("svsb200_index_create: device listed twice");
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10 || prop.minor != 0)
+            return fail("svsb200_index_create: device is not sm_100 (this binary holds sm_100a code only)");
+        std::unique_ptr<Replica> rep(new Replica());
+        rep->device = device;
+        rep->sm_count = prop.multiProcessorCount;
+        int rc = r == 0 ? upload_replica(ix.get(), rep.get(), vectors, src_stride, row_bytes, graph_rows, graph_row_len, aux)
+                        : clone_replica(ix.get(), ix->reps[0].get(), rep.get());
+        if (rc) return rc;
+        ix->reps.push_back(std::move(rep));
     }
-    if (storage == SVSB200_LVQ8) {
-        CUDA_TRY_IX(cudaMalloc(&ix->d_mean, dim * sizeof(float)));
-        CUDA_TRY_IX(cudaMemcpy(ix->d_mean, aux, dim * sizeof(float), cudaMemcpyHostToDevice));
-    }
-    CUDA_TRY_IX(cudaMalloc(&ix->d_counter, sizeof(unsigned int)));
-    CUDA_TRY_IX(cudaStreamCreateWithFlags(&ix->own_stream, cudaStreamNonBlocking));
-    CUDA_TRY_IX(cudaEventCreate(&ix->ev_start));
-    CUDA_TRY_IX(cudaEventCreate(&ix->ev_stop));
-#undef CUDA_TRY_IX
-    *out = ix;
+    *out = ix.release();
     return 0;
 }
 
+int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes,
+                         const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric, int storage,
+                         const float* aux, int device, svsb200_index** out) {
+    return svsb200_index_create_multi(vectors, dtype, n, dim, row_stride_bytes, graph_rows, graph_row_len, entry_point,
+                                      metric, storage, aux, &device, 1, out);
+}
+
 int svsb200_index_destroy(svsb200_index* ix) {
-    if (!ix) return 0;
-    cudaSetDevice(ix->device);
-    if (ix->d_vectors) cudaFree(ix->d_vectors);
-    if (ix->d_graph) cudaFree(ix->d_graph);
-    if (ix->d_ref_degree) cudaFree(ix->d_ref_degree);
-    if (ix->d_counter) cudaFree(ix->d_counter);
-    if (ix->d_mean) cudaFree(ix->d_mean);
-    ix->q_raw.release();
-    ix->q_codes.release();
-    ix->ids.release();
-    ix->q_f32.release();
-    ix->q_aux.release();
-    ix->dists.release();
-    ix->hops.release();
-    ix->evals.release();
-    ix->fetched.release();
-    if (ix->own_stream) cudaStreamDestroy(ix->own_stream);
-    if (ix->ev_start) cudaEventDestroy(ix->ev_start);
-    if (ix->ev_stop) cudaEventDestroy(ix->ev_stop);
-    delete ix;
+    delete ix;   // Replica / Scratch destructors release the device memory
     return 0;
 }
 
@@ -555,11 +676,18 @@ size_t svsb200_index_size(const svsb200_index* ix) { return ix ? ix->n : 0; }
 size_t svsb200_index_dimensions(const svsb200_index* ix) { return ix ? ix->dim : 0; }
 size_t svsb200_index_max_degree(const svsb200_index* ix) { return ix ? ix->max_degree : 0; }
 size_t svsb200_index_device_bytes(const svsb200_index* ix) { return ix ? ix->device_bytes : 0; }
-int svsb200_index_device(const svsb200_index* ix) { return ix ? ix->device : -1; }
+int svsb200_index_device(const svsb200_index* ix) { return ix && !ix->reps.empty() ? ix->reps[0]->device : -1; }
+size_t svsb200_index_num_devices(const svsb200_index* ix) { return ix ? ix->reps.size() : 0; }
 
 int svsb200_set_counting(svsb200_index* ix, int enabled) {
     if (!ix) return fail("svsb200_set_counting: NULL index");
     ix->counting = enabled;
+    return 0;
+}
+
+int svsb200_set_id_offset(svsb200_index* ix, uint64_t offset) {
+    if (!ix) return fail("svsb200_set_id_offset: NULL index");
+    ix->id_offset = offset;
     return 0;
 }
 
@@ -597,20 +725,29 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
 int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
     if (!ix || !name || !value) return fail("svsb200_get_option: NULL argument");
     const std::string key(name);
-    if (key == "last_kernel") *value = ix->last_kernel;          // 1 = lean kernel, 0 = generic kernel
-    else if (key == "warps_per_cta") *value = ix->warps_per_cta;
+    if (key == "last_kernel") {          // 1 = lean kernel, 0 = generic kernel
+        std::lock_guard<std::mutex> lock(ix->mu);
+        *value = ix->last ? ix->last->last_kernel : 0;
+    } else if (key == "warps_per_cta") *value = ix->warps_per_cta;
     else if (key == "ctas_per_sm") *value = ix->ctas_per_sm;
     else if (key == "rows_in_flight") *value = ix->rows_in_flight;
     else if (key == "visited_filter_slots") *value = ix->filter_slots;
     else if (key == "generic_kernel") *value = ix->generic_kernel;
-    else return fail("svsb200_get_option: unknown option " + key);
+    else if (key == "streams") {         // scratch sets (= streams) created so far over all replicas
+        long c = 0;
+        for (auto& rep : ix->reps) {
+            std::lock_guard<std::mutex> lock(rep->mu);
+            c += long(rep->all.size());
+        }
+        *value = c;
+    } else return fail("svsb200_get_option: unknown option " + key);
     return 0;
 }
 
-// Shared body of svsb200_search / svsb200_search_device: everything on the device.
-static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
-                            size_t capacity, void* d_out_ids, int id_bytes, float* d_out_dists, cudaStream_t stream,
-                            bool exhaustive = false) {
+// Shared body of every search entry point: everything on one device, enqueued on `stream`.
+static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const void* d_queries, int qdtype, size_t nq,
+                            size_t k, size_t window, size_t capacity, void* d_out_ids, int id_bytes, float* d_out_dists,
+                            cudaStream_t stream, bool exhaustive = false) {
     if (id_bytes != 4 && id_bytes != 8) return fail("id_bytes must be 4 or 8");
     if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
     if (window > capacity) {
@@ -647,41 +784,43 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     }
 
     const uint32_t qstride = uint32_t(round_up(ix->dim, 16));
-    CUDA_TRY(ix->q_f32.ensure(nq * qstride));
-    CUDA_TRY(ix->q_codes.ensure(nq * qstride));
-    CUDA_TRY(ix->q_aux.ensure(nq * 2));
-    if (ix->counting) {
-        CUDA_TRY(ix->hops.ensure(nq));
-        CUDA_TRY(ix->evals.ensure(nq));
-        CUDA_TRY(ix->fetched.ensure(nq));
-        ix->counted_nq = nq;
+    CUDA_TRY(sc->q_f32.ensure(nq * qstride));
+    CUDA_TRY(sc->q_codes.ensure(nq * qstride));
+    CUDA_TRY(sc->q_aux.ensure(nq * 2));
+    const bool counting = ix->counting != 0;
+    if (counting) {
+        CUDA_TRY(sc->hops.ensure(nq));
+        CUDA_TRY(sc->evals.ensure(nq));
+        CUDA_TRY(sc->fetched.ensure(nq));
+        sc->counted_nq = nq;
     }
 
     cudaError_t err;
     switch (qdtype) {
         case SVSB200_F32:
             err = launch_prepare<SVSB200_F32>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                              ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                              ix->scale, ix->bias, rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream);
             break;
         case SVSB200_F16:
             err = launch_prepare<SVSB200_F16>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                              ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                              ix->scale, ix->bias, rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream);
             break;
         case SVSB200_I8:
             err = launch_prepare<SVSB200_I8>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                             ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                             ix->scale, ix->bias, rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream);
             break;
         default:
             err = launch_prepare<SVSB200_U8>(d_queries, uint32_t(nq), uint32_t(ix->dim), qstride, mode, metric, ix->dtype,
-                                             ix->scale, ix->bias, ix->d_mean, ix->q_f32.ptr, ix->q_codes.ptr, ix->q_aux.ptr, stream);
+                                             ix->scale, ix->bias, rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream);
     }
     CUDA_TRY(err);
-    CUDA_TRY(cudaMemsetAsync(ix->d_counter, 0, sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned int), stream));
+    CUDA_TRY(cudaMemsetAsync(sc->d_cancel, 0, sizeof(int), stream));
 
     SearchParams p{};
-    p.vectors = ix->d_vectors;
-    p.graph = ix->d_graph;
-    p.ref_degree = ix->d_ref_degree;
+    p.vectors = rep->d_vectors;
+    p.graph = rep->d_graph;
+    p.ref_degree = rep->d_ref_degree;
     p.n = uint32_t(ix->n);
     p.dim = uint32_t(ix->dim);
     p.row_stride = ix->row_stride;
@@ -695,9 +834,9 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.scale = ix->scale;
     p.bias = ix->bias;
     p.scale_sq = ix->scale * ix->scale;   // EuclideanCompressed ctor (scalar.h:68-72)
-    p.qf = ix->q_f32.ptr;
-    p.qcodes = ix->q_codes.ptr;
-    p.qaux = ix->q_aux.ptr;
+    p.qf = sc->q_f32.ptr;
+    p.qcodes = sc->q_codes.ptr;
+    p.qaux = sc->q_aux.ptr;
     p.qstride = qstride;
     p.nq = uint32_t(nq);
     p.k = uint32_t(k);
@@ -707,14 +846,16 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     p.deg_pad = uint32_t(round_up(ix->gstride, 32));
     p.out_ids = d_out_ids;
     p.id_bytes = id_bytes;
+    p.id_offset = id_bytes == 8 ? ix->id_offset : 0;
     p.out_dists = d_out_dists;
-    p.work_counter = ix->d_counter;
-    p.hops = ix->counting ? ix->hops.ptr : nullptr;
-    p.evals = ix->counting ? ix->evals.ptr : nullptr;
-    p.fetched = ix->counting ? ix->fetched.ptr : nullptr;
+    p.work_counter = sc->d_counter;
+    p.cancel = sc->d_cancel;
+    p.hops = counting ? sc->hops.ptr : nullptr;
+    p.evals = counting ? sc->evals.ptr : nullptr;
+    p.fetched = counting ? sc->fetched.ptr : nullptr;
     p.filter_slots = exhaustive ? 0u : (ix->filter_slots < 0 ? 4096u : uint32_t(ix->filter_slots));
-    // 16-bit tags (two per 32-bit set, 2-way LRU) are exact as long as every id >> log2(sets) fits below
-    // the 0xFFFF "empty" mark; larger indexes fall back to direct-mapped 32-bit entries.
+    // generic kernel: 16-bit tags (two per 32-bit set, 2-way LRU) are exact as long as every id >> log2(sets) fits
+    // below the 0xFFFF "empty" mark; larger indexes fall back to direct-mapped 32-bit entries.
     p.filter_shift = 0;
     while ((2u << p.filter_shift) < p.filter_slots) ++p.filter_shift;   // log2(sets) with sets = slots / 2
     p.filter_tag16 = p.filter_slots >= 2 && ((uint64_t(ix->n - 1) >> p.filter_shift) < 0xFFFFull) && ix->filter_tag16 != 0;
@@ -740,9 +881,8 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
     const size_t fast_bytes = fast_smem_bytes(p.qstride, fast_cap_pad, p.deg_pad, fast_slots * 2u);
     const bool use_fast = !exhaustive && !ix->generic_kernel && fast_slots >= 64 && ix->filter_tag16 &&
                           (uint64_t(ix->n - 1) >> fast_shift) < 0xFFFFull && p.deg_pad <= 32u * kFastMaxGW &&
-                          p.gstride % 32u == 0 &&
-                          fast_bytes <= smem_limit;
-    ix->last_kernel = use_fast ? 1 : 0;
+                          p.gstride % 32u == 0 && fast_bytes <= smem_limit;
+    sc->last_kernel = use_fast ? 1 : 0;
     const int nrows = ix->rows_in_flight ? int(ix->rows_in_flight) : 2;
     if (use_fast) {
         p.cap_pad = fast_cap_pad;
@@ -752,7 +892,7 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
         cfg.warps_per_cta = 1;
         cfg.smem_bytes = fast_bytes;
         cfg.stream = stream;
-        cfg.grid = ix->ctas_per_sm ? ix->sm_count * int(ix->ctas_per_sm) : -ix->sm_count;
+        cfg.grid = ix->ctas_per_sm ? rep->sm_count * int(ix->ctas_per_sm) : -rep->sm_count;
     } else {
         const size_t per_warp = warp_smem_bytes(p.qstride, p.cap_pad, p.deg_pad, p.filter_slots * (p.filter_tag16 ? 2u : 4u));
         int warps = ix->warps_per_cta ? int(ix->warps_per_cta) : 4;
@@ -763,108 +903,292 @@ static int search_on_device(svsb200_index* ix, const void* d_queries, int qdtype
         cfg.stream = stream;
         // grid: persistent CTAs; the launcher clamps to what is resident.  ctas_per_sm == 0
         // means "as many as fit" (computed by the launcher through the occupancy API).
-        cfg.grid = ix->sm_count * (ix->ctas_per_sm ? int(ix->ctas_per_sm) : 0);
-        if (cfg.grid == 0 || exhaustive) cfg.grid = -ix->sm_count;   // negative: launcher multiplies by occupancy
+        cfg.grid = rep->sm_count * (ix->ctas_per_sm ? int(ix->ctas_per_sm) : 0);
+        if (cfg.grid == 0 || exhaustive) cfg.grid = -rep->sm_count;   // negative: launcher multiplies by occupancy
     }
 
-    CUDA_TRY(cudaEventRecord(ix->ev_start, stream));
+    CUDA_TRY(cudaEventRecord(sc->ev_start, stream));
+    const int rowt = ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype;
     if (exhaustive) {
-        switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
+        switch (rowt) {
             case ROW_LVQ8: err = launch_search_exhaustive<ROW_LVQ8>(op, p, cfg); break;
             case SVSB200_F32: err = launch_search_exhaustive<SVSB200_F32>(op, p, cfg); break;
             case SVSB200_F16: err = launch_search_exhaustive<SVSB200_F16>(op, p, cfg); break;
             case SVSB200_I8: err = launch_search_exhaustive<SVSB200_I8>(op, p, cfg); break;
             default: err = launch_search_exhaustive<SVSB200_U8>(op, p, cfg);
         }
-        CUDA_TRY(err);
-        CUDA_TRY(cudaEventRecord(ix->ev_stop, stream));
-        ix->timed = true;
-        return 0;
-    }
-    if (use_fast) {
-        switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
+    } else if (use_fast) {
+        switch (rowt) {
             case ROW_LVQ8: err = launch_search_fast<ROW_LVQ8>(op, p, cfg); break;
             case SVSB200_F32: err = launch_search_fast<SVSB200_F32>(op, p, cfg); break;
             case SVSB200_F16: err = launch_search_fast<SVSB200_F16>(op, p, cfg); break;
             case SVSB200_I8: err = launch_search_fast<SVSB200_I8>(op, p, cfg); break;
             default: err = launch_search_fast<SVSB200_U8>(op, p, cfg);
         }
-    } else
-    switch (ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype) {
-        case ROW_LVQ8: err = launch_search<ROW_LVQ8>(op, p, cfg, nrows); break;
-        case SVSB200_F32: err = launch_search<SVSB200_F32>(op, p, cfg, nrows); break;
-        case SVSB200_F16: err = launch_search<SVSB200_F16>(op, p, cfg, nrows); break;
-        case SVSB200_I8: err = launch_search<SVSB200_I8>(op, p, cfg, nrows); break;
-        default: err = launch_search<SVSB200_U8>(op, p, cfg, nrows);
+    } else {
+        switch (rowt) {
+            case ROW_LVQ8: err = launch_search<ROW_LVQ8>(op, p, cfg, nrows); break;
+            case SVSB200_F32: err = launch_search<SVSB200_F32>(op, p, cfg, nrows); break;
+            case SVSB200_F16: err = launch_search<SVSB200_F16>(op, p, cfg, nrows); break;
+            case SVSB200_I8: err = launch_search<SVSB200_I8>(op, p, cfg, nrows); break;
+            default: err = launch_search<SVSB200_U8>(op, p, cfg, nrows);
+        }
     }
     CUDA_TRY(err);
-    CUDA_TRY(cudaEventRecord(ix->ev_stop, stream));
-    ix->timed = true;
+    CUDA_TRY(cudaEventRecord(sc->ev_stop, stream));
+    sc->timed = true;
+    {
+        std::lock_guard<std::mutex> lock(ix->mu);
+        ix->last = sc;
+    }
     return 0;
 }
 
 int svsb200_search_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, size_t window,
                           size_t capacity, int use_visited_set, void* d_out_ids, int id_bytes, float* d_out_dists,
-                          void* stream) {
+                          void* stream_) {
     (void)use_visited_set;   // performance-only in the reference (search_buffer.h:420); results identical
     if (!ix) return fail("svsb200_search_device: NULL index");
     if (nq && (!d_queries || !d_out_ids || !d_out_dists)) return fail("svsb200_search_device: NULL buffer");
-    std::lock_guard<std::mutex> lock(ix->mutex);
-    CUDA_TRY(cudaSetDevice(ix->device));
-    return search_on_device(ix, d_queries, qdtype, nq, k, window, capacity, d_out_ids, id_bytes, d_out_dists,
-                            stream ? static_cast<cudaStream_t>(stream) : ix->own_stream);
+    if (ix->reps.size() != 1) return fail("svsb200_search_device: the index must live on exactly one device");
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    // NULL = the stream of a scratch this index keeps for that purpose (ordered against itself)
+    Scratch* sc = scratch_for_stream(rep, static_cast<cudaStream_t>(stream_), &err);
+    if (!sc) return fail(err);
+    return search_on_device(ix, rep, sc, d_queries, qdtype, nq, k, window, capacity, d_out_ids, id_bytes, d_out_dists,
+                            sc->stream);
 }
 
-int svsb200_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
-                   size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists, void* stream_) {
+// Waits for the streams of `scs`; with a cancel callback it polls the callback meanwhile and raises the device
+// flags the kernels poll per query and per hop (greedy_search.h:155, extensions.h:579).
+static int wait_all(const std::vector<Scratch*>& scs, int (*cancel)(void*), void* cancel_arg) {
+    bool raised = false;
+    for (;;) {
+        bool busy = false;
+        for (Scratch* sc : scs) {
+            cudaSetDevice(sc->device);
+            if (!cancel) {
+                CUDA_TRY(cudaStreamSynchronize(sc->stream));
+                continue;
+            }
+            cudaError_t q = cudaStreamQuery(sc->stream);
+            if (q == cudaErrorNotReady) busy = true;
+            else if (q != cudaSuccess) return fail(std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
+        }
+        if (!busy) return 0;
+        if (!raised && cancel(cancel_arg)) {
+            for (Scratch* sc : scs) {
+                cudaSetDevice(sc->device);
+                CUDA_TRY(cudaMemsetAsync(sc->d_cancel, 1, sizeof(int), sc->ctl));
+            }
+            raised = true;
+        }
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+}
+
+int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+                               size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists,
+                               void* stream_, int (*cancel)(void*), void* cancel_arg) {
     (void)use_visited_set;
     if (!ix) return fail("svsb200_search: NULL index");
     if (nq == 0) return 0;
     if (!queries || !out_ids || !out_dists) return fail("svsb200_search: NULL buffer");
     if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
     if (id_bytes != 4 && id_bytes != 8) return fail("id_bytes must be 4 or 8");
-    std::lock_guard<std::mutex> lock(ix->mutex);
-    CUDA_TRY(cudaSetDevice(ix->device));
-    cudaStream_t stream = stream_ ? static_cast<cudaStream_t>(stream_) : ix->own_stream;
-    const size_t qbytes = nq * ix->dim * esize(qdtype);
-    CUDA_TRY(ix->q_raw.ensure(qbytes));
-    CUDA_TRY(ix->ids.ensure(nq * k * size_t(id_bytes)));
-    CUDA_TRY(ix->dists.ensure(nq * k));
-    CUDA_TRY(cudaMemcpyAsync(ix->q_raw.ptr, queries, qbytes, cudaMemcpyHostToDevice, stream));
-    int rc = search_on_device(ix, ix->q_raw.ptr, qdtype, nq, k, window, capacity, ix->ids.ptr, id_bytes, ix->dists.ptr,
-                              stream);
-    if (rc) return rc;
-    CUDA_TRY(cudaMemcpyAsync(out_ids, ix->ids.ptr, nq * k * size_t(id_bytes), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaMemcpyAsync(out_dists, ix->dists.ptr, nq * k * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    CUDA_TRY(cudaStreamSynchronize(stream));
-    return 0;
+    const size_t R = ix->reps.size();
+    if (stream_ && R != 1) return fail("svsb200_search: a caller stream needs a single-device index");
+    if (cancel && cancel(cancel_arg)) return 0;   // index.h:575 checks before any work
+    const size_t qrow = ix->dim * esize(qdtype);
+    std::vector<Scratch*> used;
+    std::vector<Replica*> used_rep;
+    int rc = 0;
+    for (size_t r = 0; r < R && rc == 0; ++r) {
+        size_t lo, hi;
+        balance(nq, R, r, &lo, &hi);
+        if (hi == lo) continue;
+        Replica* rep = ix->reps[r].get();
+        cudaError_t e = cudaSetDevice(rep->device);
+        if (e != cudaSuccess) {
+            rc = fail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+            break;
+        }
+        std::string err;
+        Scratch* sc = stream_ ? scratch_for_stream(rep, static_cast<cudaStream_t>(stream_), &err) : acquire(rep, &err);
+        if (!sc) {
+            rc = fail(err);
+            break;
+        }
+        used.push_back(sc);
+        used_rep.push_back(stream_ ? nullptr : rep);
+        const size_t m = hi - lo;
+        auto step = [&]() -> int {
+            CUDA_TRY(sc->q_raw.ensure(m * qrow));
+            CUDA_TRY(sc->ids.ensure(m * k * size_t(id_bytes)));
+            CUDA_TRY(sc->dists.ensure(m * k));
+            CUDA_TRY(cudaMemcpyAsync(sc->q_raw.ptr, static_cast<const char*>(queries) + lo * qrow, m * qrow,
+                                     cudaMemcpyHostToDevice, sc->stream));
+            int rc2 = search_on_device(ix, rep, sc, sc->q_raw.ptr, qdtype, m, k, window, capacity, sc->ids.ptr, id_bytes,
+                                       sc->dists.ptr, sc->stream);
+            if (rc2) return rc2;
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_ids) + lo * k * size_t(id_bytes), sc->ids.ptr,
+                                     m * k * size_t(id_bytes), cudaMemcpyDeviceToHost, sc->stream));
+            CUDA_TRY(cudaMemcpyAsync(out_dists + lo * k, sc->dists.ptr, m * k * sizeof(float), cudaMemcpyDeviceToHost,
+                                     sc->stream));
+            return 0;
+        };
+        rc = step();
+    }
+    const std::string first_error = g_error;
+    int rc_wait = wait_all(used, cancel, cancel_arg);
+    for (size_t i = 0; i < used.size(); ++i)
+        if (used_rep[i]) release(used_rep[i], used[i]);
+    if (rc) {
+        g_error = first_error;
+        return rc;
+    }
+    return rc_wait;
+}
+
+int svsb200_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+                   size_t capacity, int use_visited_set, void* out_ids, int id_bytes, float* out_dists, void* stream_) {
+    return svsb200_search_cancellable(ix, queries, qdtype, nq, k, window, capacity, use_visited_set, out_ids, id_bytes,
+                                      out_dists, stream_, nullptr, nullptr);
+}
+
+int svsb200_search_sharded(svsb200_index* const* shards, size_t nshards, const void* queries, int qdtype, size_t nq,
+                           size_t k, size_t window, size_t capacity, uint64_t* out_ids, float* out_dists) {
+    if (!shards || nshards == 0) return fail("svsb200_search_sharded: no shards");
+    if (nshards > 1024) return fail("svsb200_search_sharded: at most 1024 shards");
+    if (nq == 0) return 0;
+    if (!queries || !out_ids || !out_dists) return fail("svsb200_search_sharded: NULL buffer");
+    if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
+    for (size_t s = 0; s < nshards; ++s) {
+        if (!shards[s] || shards[s]->reps.size() != 1) return fail("svsb200_search_sharded: every shard is a single-device index");
+        if (shards[s]->dim != shards[0]->dim || shards[s]->metric != shards[0]->metric)
+            return fail("svsb200_search_sharded: shards disagree on dimension or metric");
+    }
+    const size_t qbytes = nq * shards[0]->dim * esize(qdtype);
+    const size_t cnt = nq * k;
+    std::vector<Scratch*> scs(nshards, nullptr);
+    std::string err;
+    auto give_back = [&]() {
+        for (size_t s = 0; s < nshards; ++s)
+            if (scs[s]) release(shards[s]->reps[0].get(), scs[s]);
+    };
+    for (size_t s = 0; s < nshards; ++s) {
+        Replica* rep = shards[s]->reps[0].get();
+        cudaSetDevice(rep->device);
+        scs[s] = acquire(rep, &err);
+        if (!scs[s]) {
+            give_back();
+            return fail(err);
+        }
+    }
+    // the merging device is shard 0's; its scratch holds the [nshards][nq][k] gather block
+    Replica* rep0 = shards[0]->reps[0].get();
+    Scratch* sc0 = scs[0];
+    auto body = [&]() -> int {
+        CUDA_TRY(cudaSetDevice(rep0->device));
+        CUDA_TRY(sc0->gather_ids.ensure(nshards * cnt));
+        CUDA_TRY(sc0->gather_dists.ensure(nshards * cnt));
+        CUDA_TRY(sc0->merged_ids.ensure(cnt));
+        CUDA_TRY(sc0->merged_dists.ensure(cnt));
+        for (size_t s = 0; s < nshards; ++s) {
+            Replica* rep = shards[s]->reps[0].get();
+            Scratch* sc = scs[s];
+            CUDA_TRY(cudaSetDevice(rep->device));
+            CUDA_TRY(sc->q_raw.ensure(qbytes));
+            CUDA_TRY(cudaMemcpyAsync(sc->q_raw.ptr, queries, qbytes, cudaMemcpyHostToDevice, sc->stream));
+            // With peer access the shard's kernel writes its rows straight into the merging device's block over
+            // NVLink (the gather is fused into the search kernel's copy-out); otherwise it writes locally and the
+            // block is moved by a peer copy.
+            bool direct = rep->device == rep0->device;
+            if (!direct) {
+                int can = 0;
+                if (cudaDeviceCanAccessPeer(&can, rep->device, rep0->device) == cudaSuccess && can) {
+                    cudaError_t pe = cudaDeviceEnablePeerAccess(rep0->device, 0);
+                    direct = pe == cudaSuccess || pe == cudaErrorPeerAccessAlreadyEnabled;
+                    cudaGetLastError();
+                }
+            }
+            uint64_t* ids_dst = sc0->gather_ids.ptr + s * cnt;
+            float* d_dst = sc0->gather_dists.ptr + s * cnt;
+            if (!direct) {
+                CUDA_TRY(sc->ids.ensure(cnt * 8));
+                CUDA_TRY(sc->dists.ensure(cnt));
+            }
+            int rc = search_on_device(shards[s], rep, sc, sc->q_raw.ptr, qdtype, nq, k, window, capacity,
+                                      direct ? static_cast<void*>(ids_dst) : static_cast<void*>(sc->ids.ptr), 8,
+                                      direct ? d_dst : sc->dists.ptr, sc->stream);
+            if (rc) return rc;
+            CUDA_TRY(cudaEventRecord(sc->ev_done, sc->stream));
+            if (s != 0) {
+                CUDA_TRY(cudaSetDevice(rep0->device));
+                CUDA_TRY(cudaStreamWaitEvent(sc0->stream, sc->ev_done, 0));
+                if (!direct) {
+                    CUDA_TRY(cudaMemcpyPeerAsync(ids_dst, rep0->device, sc->ids.ptr, rep->device, cnt * 8, sc0->stream));
+                    CUDA_TRY(cudaMemcpyPeerAsync(d_dst, rep0->device, sc->dists.ptr, rep->device, cnt * 4, sc0->stream));
+                }
+            }
+        }
+        CUDA_TRY(cudaSetDevice(rep0->device));
+        const unsigned warps = 4;
+        merge_topk_kernel<<<unsigned((nq + warps - 1) / warps), warps * 32, 0, sc0->stream>>>(
+            sc0->gather_ids.ptr, sc0->gather_dists.ptr, uint32_t(nshards), uint32_t(nq), uint32_t(k),
+            shards[0]->metric != SVSB200_L2, sc0->merged_ids.ptr, sc0->merged_dists.ptr);
+        count_launch();
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(out_ids, sc0->merged_ids.ptr, cnt * 8, cudaMemcpyDeviceToHost, sc0->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_dists, sc0->merged_dists.ptr, cnt * 4, cudaMemcpyDeviceToHost, sc0->stream));
+        return 0;
+    };
+    int rc = body();
+    const std::string first_error = g_error;
+    int rc_wait = wait_all(scs, nullptr, nullptr);
+    give_back();
+    if (rc) {
+        g_error = first_error;
+        return rc;
+    }
+    return rc_wait;
+}
+
+static Scratch* last_scratch(svsb200_index* ix) {
+    std::lock_guard<std::mutex> lock(ix->mu);
+    return ix->last;
 }
 
 int svsb200_get_fetched(svsb200_index* ix, size_t nq, uint32_t* fetched) {
     if (!ix || !fetched) return fail("svsb200_get_fetched: NULL argument");
-    if (!ix->counting || ix->counted_nq < nq) return fail("svsb200_get_fetched: counting was not enabled for that many queries");
-    CUDA_TRY(cudaSetDevice(ix->device));
+    Scratch* sc = last_scratch(ix);
+    if (!ix->counting || !sc || sc->counted_nq < nq) return fail("svsb200_get_fetched: counting was not enabled for that many queries");
+    CUDA_TRY(cudaSetDevice(sc->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(fetched, ix->fetched.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(fetched, sc->fetched.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
 int svsb200_get_counters(svsb200_index* ix, size_t nq, uint32_t* hops, uint32_t* evals) {
     if (!ix) return fail("svsb200_get_counters: NULL index");
-    if (!ix->counting || ix->counted_nq < nq) return fail("svsb200_get_counters: counting was not enabled for that many queries");
-    CUDA_TRY(cudaSetDevice(ix->device));
+    Scratch* sc = last_scratch(ix);
+    if (!ix->counting || !sc || sc->counted_nq < nq) return fail("svsb200_get_counters: counting was not enabled for that many queries");
+    CUDA_TRY(cudaSetDevice(sc->device));
     CUDA_TRY(cudaDeviceSynchronize());
-    if (hops) CUDA_TRY(cudaMemcpy(hops, ix->hops.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    if (evals) CUDA_TRY(cudaMemcpy(evals, ix->evals.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (hops) CUDA_TRY(cudaMemcpy(hops, sc->hops.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (evals) CUDA_TRY(cudaMemcpy(evals, sc->evals.ptr, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 
 int svsb200_last_kernel_ms(svsb200_index* ix, float* ms) {
     if (!ix || !ms) return fail("svsb200_last_kernel_ms: NULL argument");
-    if (!ix->timed) return fail("svsb200_last_kernel_ms: no search has run yet");
-    CUDA_TRY(cudaSetDevice(ix->device));
-    CUDA_TRY(cudaEventSynchronize(ix->ev_stop));
-    CUDA_TRY(cudaEventElapsedTime(ms, ix->ev_start, ix->ev_stop));
+    Scratch* sc = last_scratch(ix);
+    if (!sc || !sc->timed) return fail("svsb200_last_kernel_ms: no search has run yet");
+    CUDA_TRY(cudaSetDevice(sc->device));
+    CUDA_TRY(cudaEventSynchronize(sc->ev_stop));
+    CUDA_TRY(cudaEventElapsedTime(ms, sc->ev_start, sc->ev_stop));
     return 0;
 }
 
@@ -913,14 +1237,17 @@ int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* 
 }
 
 int svsb200_exhaustive_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, uint64_t* d_out_ids,
-                              float* d_out_dists, void* stream) {
+                              float* d_out_dists, void* stream_) {
     if (!ix) return fail("svsb200_exhaustive_device: NULL index");
     if (nq && (!d_queries || !d_out_ids || !d_out_dists)) return fail("svsb200_exhaustive_device: NULL buffer");
     if (k == 0 || k > 1024) return fail("svsb200_exhaustive_device: k must be in [1, 1024]");
-    std::lock_guard<std::mutex> lock(ix->mutex);
-    CUDA_TRY(cudaSetDevice(ix->device));
-    return search_on_device(ix, d_queries, qdtype, nq, k, k, k, d_out_ids, 8, d_out_dists,
-                            stream ? static_cast<cudaStream_t>(stream) : ix->own_stream, true);
+    if (ix->reps.size() != 1) return fail("svsb200_exhaustive_device: the index must live on exactly one device");
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    Scratch* sc = scratch_for_stream(rep, static_cast<cudaStream_t>(stream_), &err);
+    if (!sc) return fail(err);
+    return search_on_device(ix, rep, sc, d_queries, qdtype, nq, k, k, k, d_out_ids, 8, d_out_dists, sc->stream, true);
 }
 
 }  // extern "C"

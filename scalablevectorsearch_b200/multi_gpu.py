@@ -40,44 +40,60 @@ def _world(group) -> tuple[int, int]:
     return 0, 1
 
 
-def _gather_rows(local: torch.Tensor, counts: list[int], group) -> torch.Tensor:
-    """All-gather row blocks of unequal length (sizes known from ``balance``) into one tensor."""
-    rank, world = _world(group)
-    if world == 1:
-        return local
-    width = max(counts)
-    padded = local
-    if local.shape[0] < width:
-        pad = torch.zeros((width - local.shape[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-        padded = torch.cat([local, pad], dim=0)
-    out = torch.empty((world * width,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded.contiguous(), group=group)
-    if all(c == width for c in counts):
-        return out
-    return torch.cat([out[r * width: r * width + counts[r]] for r in range(world)], dim=0)
-
-
 class ReplicatedSearch:
-    """Mode A: replicate the index, shard the queries, gather the result rows."""
+    """Mode A: replicate the index, shard the queries, gather the result rows.
 
-    def __init__(self, local_search: Callable[[torch.Tensor, int], tuple[torch.Tensor, torch.Tensor]], group=None):
-        """``local_search(queries, k) -> (ids int64 [m,k], dists float32 [m,k])`` on this rank's device."""
+    One collective per batch and nothing else on the data path: every rank owns a byte block
+    ``[ids | distances]`` of ``width = max rows per rank`` rows; the local search writes its rows straight into
+    that block when the callable takes ``out=`` (the CUDA path does), and one ``all_gather_into_tensor`` of the
+    blocks (NCCL over NVLink) completes the batch -- no concatenation, no widening of the float distances."""
+
+    def __init__(self, local_search: Callable[..., tuple[torch.Tensor, torch.Tensor]], group=None,
+                 id_dtype: torch.dtype = torch.int64):
+        """``local_search(queries, k[, out=(ids, dists)]) -> (ids [m,k], dists float32 [m,k])`` on this rank's
+        device; ``id_dtype`` is the id element type of the gathered result (int64, or int32 to halve the bytes)."""
         self.local_search = local_search
         self.group = group
+        self.id_dtype = id_dtype
+        self._takes_out = bool(getattr(local_search, "takes_out", False))
+        self._blocks = {}
+
+    def _buffers(self, world, width, k, device):
+        key = (world, width, k, str(device))
+        if key not in self._blocks:
+            isz = torch.empty((), dtype=self.id_dtype).element_size()
+            nb_ids, nb_d = width * k * isz, width * k * 4
+            mine = torch.empty(nb_ids + nb_d, dtype=torch.uint8, device=device)
+            everyone = torch.empty(world * (nb_ids + nb_d), dtype=torch.uint8, device=device)
+            self._blocks = {key: (mine, everyone, nb_ids)}   # keep only the current shape
+        return self._blocks[key]
 
     def search(self, queries: torch.Tensor, k: int) -> tuple[torch.Tensor, torch.Tensor]:
         rank, world = _world(self.group)
         nq = queries.shape[0]
         start, stop = balance(nq, world, rank)
-        ids, dists = self.local_search(queries[start:stop], k)
+        m = stop - start
         if world == 1:
-            return ids, dists
+            return self.local_search(queries, k)
         counts = [balance(nq, world, r)[1] - balance(nq, world, r)[0] for r in range(world)]
-        # one collective for both result arrays: ids and the float32 distances (bit-cast, widened to
-        # int64 lanes) travel as a single [rows, 2k] int64 block -- the gather is latency bound
-        packed = torch.cat([ids, dists.view(torch.int32).to(torch.int64)], dim=1)
-        out = _gather_rows(packed, counts, self.group)
-        return out[:, :k].contiguous(), out[:, k:].to(torch.int32).view(torch.float32)
+        width = max(counts)
+        mine, everyone, nb_ids = self._buffers(world, width, k, queries.device)
+        ids_v = mine[:nb_ids].view(self.id_dtype).view(width, k)
+        d_v = mine[nb_ids:].view(torch.float32).view(width, k)
+        if self._takes_out:
+            self.local_search(queries[start:stop], k, out=(ids_v[:m], d_v[:m]))
+        else:
+            ids, dists = self.local_search(queries[start:stop], k)
+            ids_v[:m].copy_(ids)
+            d_v[:m].copy_(dists)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        blocks = everyone.view(world, -1)
+        all_ids = blocks[:, :nb_ids].view(self.id_dtype).view(world, width, k)
+        all_d = blocks[:, nb_ids:].view(torch.float32).view(world, width, k)
+        if all(c == width for c in counts):
+            return all_ids.reshape(world * width, k), all_d.reshape(world * width, k)
+        return (torch.cat([all_ids[r, :counts[r]] for r in range(world)], dim=0),
+                torch.cat([all_d[r, :counts[r]] for r in range(world)], dim=0))
 
 
 def merge_topk_reference_order(ids: np.ndarray, dists: np.ndarray, k: int, greater: bool):
@@ -153,14 +169,19 @@ def cuda_local_search(index, id_dtype=torch.int64):
         raise TypeError("id_dtype must be torch.int32 or torch.int64")
     id_bytes = 4 if id_dtype == torch.int32 else 8
 
-    def run(queries: torch.Tensor, k: int):
+    def run(queries: torch.Tensor, k: int, out=None):
         assert queries.is_cuda and queries.is_contiguous()
         nq = queries.shape[0]
-        ids = torch.empty((nq, k), dtype=id_dtype, device=queries.device)
-        dists = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        if out is None:
+            ids = torch.empty((nq, k), dtype=id_dtype, device=queries.device)
+            dists = torch.empty((nq, k), dtype=torch.float32, device=queries.device)
+        else:
+            ids, dists = out
+            assert ids.dtype == id_dtype and ids.is_contiguous() and dists.is_contiguous() and ids.shape == (nq, k)
         if nq:
             index.search_device(queries.data_ptr(), np_dtype[queries.dtype], nq, k, ids.data_ptr(), dists.data_ptr(),
                                 stream=_stream_handle(queries.device), id_bytes=id_bytes)
         return ids, dists
 
+    run.takes_out = True
     return run

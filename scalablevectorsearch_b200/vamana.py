@@ -142,12 +142,14 @@ class Vamana:
 
     @classmethod
     def from_arrays(cls, data: np.ndarray, graph: np.ndarray, entry_point: int,
-                    distance: DistanceType = DistanceType.L2, device: int = 0, sq: tuple | None = None,
+                    distance: DistanceType = DistanceType.L2, device=0, sq: tuple | None = None,
                     num_threads: int = 1, lvq8: tuple | None = None) -> "Vamana":
         """Assemble from in-memory parts: ``VamanaIndex(graph, data, entry_point, distance, threads)``
         (index/vamana/index.h:364-378).  ``graph`` is ``uint32[n][max_degree+1]``, degree first.
         ``sq=(scale, bias)`` marks ``data`` as scalar-quantised int8/uint8 codes;
-        ``lvq8=(dim, mean)`` marks ``data`` as LVQ-8 rows from :func:`lvq8_compress`."""
+        ``lvq8=(dim, mean)`` marks ``data`` as LVQ-8 rows from :func:`lvq8_compress`.
+        ``device`` is one CUDA ordinal or a list of them: a list replicates the index and every batch is
+        split over the devices with the reference's ``threads::balance`` (one process, no collective)."""
         self = cls.__new__(cls)
         self._init(data, graph, entry_point, distance, device, num_threads, sq, lvq8)
         return self
@@ -177,10 +179,12 @@ class Vamana:
             dim, mean = int(lvq8[0]), np.ascontiguousarray(lvq8[1], dtype=np.float32)
             aux = (C.c_float * dim)(*mean.tolist())
             storage, stride = _STORAGE_LVQ8, data.shape[1]
-        _lib.check(self._lib.svsb200_index_create(
+        devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+        dev_arr = (C.c_int * len(devices))(*devices)
+        _lib.check(self._lib.svsb200_index_create_multi(
             data.ctypes.data, _DTYPE_CODE[data.dtype], data.shape[0], dim, stride, graph.ctypes.data,
             graph.shape[1], int(entry_point), int(self._distance), storage,
-            C.cast(aux, C.c_void_p) if aux is not None else None, int(device), C.byref(handle)))
+            C.cast(aux, C.c_void_p) if aux is not None else None, dev_arr, len(devices), C.byref(handle)))
         self._h = handle
 
     def __del__(self):
@@ -233,8 +237,15 @@ class Vamana:
         return self._lib.svsb200_index_device_bytes(self._h)
 
     # ---- search ------------------------------------------------------------------------
-    def search(self, queries: np.ndarray, n_neighbors: int):
-        """``svs.Vamana.search(queries, n_neighbors)`` -> (ids uint64 [nq,k], distances float32 [nq,k])."""
+    @property
+    def num_devices(self) -> int:
+        return self._lib.svsb200_index_num_devices(self._h)
+
+    def search(self, queries: np.ndarray, n_neighbors: int, cancel=None):
+        """``svs.Vamana.search(queries, n_neighbors)`` -> (ids uint64 [nq,k], distances float32 [nq,k]).
+        ``cancel`` is an optional zero-argument predicate, polled while the batch runs (the reference's
+        ``lib::DefaultPredicate`` of index/vamana/index.h:568): once it returns True the kernels stop at their
+        next query / hop boundary and the rows of unfinished queries are unspecified."""
         q = np.ascontiguousarray(queries)
         if q.ndim != 2:
             raise ValueError("queries must be a 2-D array")
@@ -246,9 +257,17 @@ class Vamana:
         ids = np.empty((nq, k), dtype=np.uint64)
         dists = np.empty((nq, k), dtype=np.float32)
         cfg = self._params.buffer_config
-        _lib.check(self._lib.svsb200_search(
-            self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k, cfg.search_window_size, cfg.search_buffer_capacity,
-            int(self._params.search_buffer_visited_set), ids.ctypes.data, 8, dists.ctypes.data, None))
+        if cancel is None:
+            _lib.check(self._lib.svsb200_search(
+                self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k, cfg.search_window_size,
+                cfg.search_buffer_capacity, int(self._params.search_buffer_visited_set), ids.ctypes.data, 8,
+                dists.ctypes.data, None))
+        else:
+            fn = _lib.CANCEL_FN(lambda _arg: 1 if cancel() else 0)
+            _lib.check(self._lib.svsb200_search_cancellable(
+                self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k, cfg.search_window_size,
+                cfg.search_buffer_capacity, int(self._params.search_buffer_visited_set), ids.ctypes.data, 8,
+                dists.ctypes.data, None, fn, None))
         return ids, dists
 
     def search_device(self, d_queries: int, qdtype: np.dtype, nq: int, n_neighbors: int, d_ids: int, d_dists: int,
@@ -294,3 +313,37 @@ class Vamana:
         out = C.c_long()
         _lib.check(self._lib.svsb200_get_option(self._h, name.encode(), C.byref(out)))
         return int(out.value)
+
+
+class ShardedVamana:
+    """One dataset split into contiguous id ranges, one single-device :class:`Vamana` (own graph, own entry
+    point) per range -- SURVEY.md 8e mode B inside one process (``svsb200_search_sharded``).  Every query runs
+    on every shard; the per-shard top-k rows are gathered on the first shard's device over NVLink and merged
+    with the reference's ``TotalOrder`` (distance, then id; lib/neighbor.h:143-155)."""
+
+    def __init__(self, shards: list, id_offsets: list):
+        if len(shards) != len(id_offsets) or not shards:
+            raise ValueError("one id offset per shard")
+        self._shards = list(shards)
+        self._lib = _lib.lib()
+        for sh, off in zip(self._shards, id_offsets):
+            _lib.check(self._lib.svsb200_set_id_offset(sh._h, int(off)))
+        self.search_parameters = VamanaSearchParameters()
+
+    @property
+    def size(self) -> int:
+        return sum(sh.size for sh in self._shards)
+
+    def search(self, queries: np.ndarray, n_neighbors: int):
+        q = np.ascontiguousarray(queries)
+        if q.ndim != 2 or q.shape[1] != self._shards[0].dimensions:
+            raise ValueError("queries must be [nq, dim]")
+        nq, k = q.shape[0], int(n_neighbors)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        cfg = self.search_parameters.buffer_config
+        handles = (C.c_void_p * len(self._shards))(*[sh._h for sh in self._shards])
+        _lib.check(self._lib.svsb200_search_sharded(handles, len(self._shards), q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k,
+                                                    cfg.search_window_size, cfg.search_buffer_capacity,
+                                                    ids.ctypes.data, dists.ctypes.data))
+        return ids, dists

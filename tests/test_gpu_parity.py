@@ -371,3 +371,84 @@ def test_merge_topk_device_is_the_total_order(shards, greater):
     torch.cuda.synchronize()
     assert np.array_equal(got_i.cpu().numpy(), want_i)
     assert np.array_equal(got_d.cpu().numpy() + 0.0, want_d + 0.0)   # +0.0: -0 and +0 compare equal
+
+
+def test_concurrent_host_threads_get_their_own_streams(dataset, ref_outputs):
+    """"threadpool -> CUDA streams": several host threads search one index at once (the reference allows this with
+    external scratch, index/vamana/index.h:455-470); every call checks out its own stream + scratch."""
+    import threading
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    from scalablevectorsearch_b200 import SearchBufferConfig
+    index.search_parameters.buffer_config = SearchBufferConfig(22, 23)
+    q = np.tile(dataset.queries[100:], (8, 1))
+    results, errors = {}, []
+
+    def work(i):
+        try:
+            for _ in range(4):
+                results[i] = index.search(q, 10)
+        except Exception as e:   # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors, errors
+    for i in range(4):
+        for b in range(8):
+            assert_same((results[i][0][900 * b:900 * (b + 1)], results[i][1][900 * b:900 * (b + 1)]),
+                        ref_outputs["l2_f32_f32_w22_c23_ids"], ref_outputs["l2_f32_f32_w22_c23_dists"], f"thread {i}")
+    assert index.get_option("streams") >= 2
+
+
+def test_cancellation_predicate(dataset, ref_outputs):
+    """`cancel` (index/vamana/index.h:568, polled at greedy_search.h:155 / extensions.h:579): a predicate that is
+    already true returns before any work; one that never fires leaves the results untouched; one that fires while
+    the batch runs makes the call return early (rows of unfinished queries are unspecified)."""
+    import time
+    from scalablevectorsearch_b200 import SearchBufferConfig
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    index.search_parameters.buffer_config = SearchBufferConfig(22, 23)
+    got = index.search(dataset.queries[100:], 10, cancel=lambda: False)
+    assert_same(got, ref_outputs["l2_f32_f32_w22_c23_ids"], ref_outputs["l2_f32_f32_w22_c23_dists"], "cancel never")
+    ids, _ = index.search(dataset.queries[100:], 10, cancel=lambda: True)
+    assert ids.shape == (900, 10)
+    # a long batch (large window, many queries): cancel after the first poll, compare with the uncancelled time
+    index.search_parameters.buffer_config = SearchBufferConfig(400, 400)
+    q = np.tile(dataset.queries, (300, 1))
+    t0 = time.perf_counter()
+    index.search(q, 10)
+    full = time.perf_counter() - t0
+    calls = []
+
+    def fire():
+        calls.append(1)
+        return len(calls) > 2
+    t0 = time.perf_counter()
+    index.search(q, 10, cancel=fire)
+    cancelled = time.perf_counter() - t0
+    assert len(calls) > 2
+    assert cancelled < 0.7 * full, (cancelled, full)
+
+
+def test_sharded_index_in_one_process_matches_reference_per_shard_plus_merge(dataset, oracle):
+    """svsb200_search_sharded (mode B, single process): two shards on the same device here (the multi-GPU form
+    differs only in where the shards live) == oracle per shard + TotalOrder merge."""
+    from scalablevectorsearch_b200 import SearchBufferConfig, ShardedVamana
+    from scalablevectorsearch_b200.multi_gpu import merge_topk_reference_order
+    rng = np.random.default_rng(5)
+    x = dataset.data
+    n = x.shape[0]
+    cuts = [0, 3300, 7100, n]
+    shards, parts = [], []
+    q = dataset.queries[:128]
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        g = knn_graph(x[a:b], 24, rng)
+        sh = make_index(x[a:b], g, 5, "l2")
+        shards.append(sh)
+        wi, wd = oracle.index(x[a:b], g, 5, "l2").search(q, 10, 32, 48)
+        parts.append((wi.astype(np.int64) + a, wd))
+    sv = ShardedVamana(shards, cuts[:-1])
+    sv.search_parameters.buffer_config = SearchBufferConfig(32, 48)
+    ids, dists = sv.search(q, 10)
+    want_i, want_d = merge_topk_reference_order(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), 10, False)
+    assert np.array_equal(ids.astype(np.int64), want_i) and np.array_equal(bits(dists), bits(want_d))
