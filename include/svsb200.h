@@ -187,6 +187,22 @@ size_t svsb200_lvq8_row_stride(size_t dim);
 int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows,
                           int device);
 
+/* GPU graph construction.  Replaces: index::vamana::auto_build / VamanaIndex(VamanaBuildParameters, ...)
+ * (include/svs/index/vamana/index.h:404-440,968-994) and VamanaBuilder::construct
+ * (index/vamana/vamana_build.h:221-599): medoid entry point (core/medioid.h:292-330), two passes over
+ * batches of max(40, n/4096) rounds, greedy search with full search history + alpha-robust pruning
+ * (prune.h: Progressive strategy for L2, Iterative for MIP), reverse edges with overflow re-pruning to
+ * `prune_to`.  Arguments are VamanaBuildParameters (index/vamana/build_params.h): 0 selects the reference's
+ * default (alpha 1.2 / 0.95, max_candidate_pool_size = 3 * window_size, prune_to = max_degree - 4).
+ *   vectors     n x dim float32 / float16 rows in HOST memory (row_stride_bytes apart, 0 = dense);
+ *   graph_rows_out  uint32[n][graph_max_degree + 1], the reference's in-memory layout (degree first), HOST;
+ * The reference's result depends on thread timing, so parity is its own bar: recall equivalence of the
+ * built index (tests/integration/vamana/index_build.cpp:96,139-140). */
+int svsb200_build_vamana(
+    const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes, int metric,
+    float alpha, size_t graph_max_degree, size_t window_size, size_t max_candidate_pool_size,
+    size_t prune_to, int device, uint32_t* graph_rows_out, uint32_t* entry_point_out);
+
 /* Exhaustive search used by the harness for ground truth (replaces svs::Flat /
  * index/flat/flat.h:159 for recall measurement only): top-k of every query against all
  * `n` base vectors already on the device inside `index`. Distances use the same exact

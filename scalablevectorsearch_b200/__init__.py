@@ -5,8 +5,8 @@ the host-side mirror of the reference's search interface (:mod:`.vamana`), and t
 around it (:mod:`.io`).
 """
 from .vamana import (DataType, DistanceType, GraphLoader, SearchBufferConfig, ShardedVamana, Vamana,
-                     VamanaSearchParameters, VectorDataLoader, lvq8_compress)
+                     VamanaBuildParameters, VamanaSearchParameters, VectorDataLoader, build_graph, lvq8_compress)
 from ._lib import Svsb200Error
 
 __all__ = ["DataType", "DistanceType", "GraphLoader", "SearchBufferConfig", "Vamana", "VamanaSearchParameters",
-           "VectorDataLoader", "Svsb200Error", "lvq8_compress", "ShardedVamana"]
+           "VectorDataLoader", "Svsb200Error", "lvq8_compress", "ShardedVamana", "VamanaBuildParameters", "build_graph"]

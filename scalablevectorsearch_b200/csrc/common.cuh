@@ -69,6 +69,10 @@ struct SearchParams {
     uint32_t* evals;
     uint32_t* fetched;           // rows actually read from HBM (after the visited filter)
     const int* cancel;           // optional device flag: non-zero stops the batch (polled per query and per hop)
+    // graph builder only (HIST kernels): per query, every expanded node {key bits, id}
+    uint2* hist;
+    uint32_t* hist_count;
+    uint32_t hist_cap;
 };
 
 struct LaunchConfig {
@@ -105,5 +109,6 @@ template <int ROWT> cudaError_t launch_search_fast(int op, const SearchParams& p
 template <int ROWT> cudaError_t launch_search_exhaustive(int op, const SearchParams& p, const LaunchConfig& cfg);
 
 void count_launch();
+int set_error(const std::string& msg);   // records the calling thread's svsb200_last_error(); returns 1
 
 }  // namespace svsb200

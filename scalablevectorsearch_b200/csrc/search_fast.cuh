@@ -39,7 +39,9 @@ template <int ROWT, int OP, int DS, int KS> constexpr int fast_min_blocks() {
 #endif
 }
 
-template <int ROWT, int OP, int DS, int KS>
+// HIST = true is the graph builder's form (build.cu): every expanded node is appended, with its key, to the
+// query's search history -- the reference's `use_full_search_history` candidate pool (vamana_build.h:344-352).
+template <int ROWT, int OP, int DS, int KS, bool HIST = false>
 __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vamana_search_fast_kernel(const __grid_constant__ SearchParams p) {
     constexpr int NROWS = 2;
     constexpr bool kInt = (OP >= OP_L2I);
@@ -94,6 +96,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
         // ---- EntryPointInitializer (greedy_search.h:62-94): the entry point goes through the same
         // evaluate-and-merge code as a hop's neighbours, into the empty buffer ----
         uint32_t size = 0, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
+        uint32_t n_hist = 0;
         uint32_t staged_node = NONE;          // node whose adjacency row sits in nxt[]
         uint32_t nxt[kFastMaxGW];
 #pragma unroll
@@ -156,6 +159,10 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                     if (w * 32u < p.gstride) nxt[w] = __ldg(prow + w * 32u + lane);
             }
             if (lane == 0) buf[pos].y = node | kVisitedBit;
+            if constexpr (HIST) {
+                if (lane == 0 && n_hist < p.hist_cap) p.hist[size_t(q) * p.hist_cap + n_hist] = make_uint2(buf[pos].x, node);
+                n_hist += (n_hist < p.hist_cap) ? 1u : 0u;
+            }
             cursor = pos + 1;
 
             // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
@@ -337,13 +344,16 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             p.evals[q] = n_evals;
             p.fetched[q] = n_fetched;
         }
+        if constexpr (HIST) {
+            if (lane == 0) p.hist_count[q] = n_hist;
+        }
         __syncwarp();
     }
 }
 
-template <int ROWT, int OP, int DS, int KS = 1>
+template <int ROWT, int OP, int DS, int KS = 1, bool HIST = false>
 cudaError_t launch_fast(const SearchParams& p, const LaunchConfig& cfg) {
-    auto kernel = vamana_search_fast_kernel<ROWT, OP, DS, KS>;
+    auto kernel = vamana_search_fast_kernel<ROWT, OP, DS, KS, HIST>;
     cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(cfg.smem_bytes));
     if (err != cudaSuccess) return err;
     int grid = cfg.grid;
@@ -360,15 +370,15 @@ cudaError_t launch_fast(const SearchParams& p, const LaunchConfig& cfg) {
     return cudaGetLastError();
 }
 
-template <int ROWT, int OP> cudaError_t launch_fast_dims(const SearchParams& p, const LaunchConfig& cfg) {
+template <int ROWT, int OP, bool HIST = false> cudaError_t launch_fast_dims(const SearchParams& p, const LaunchConfig& cfg) {
     // Static dimensions get fully unrolled loads; everything else takes the dynamic-length path.  Same
     // expression tree either way, like the reference's static-N vs Dynamic kernels (distance_core.h:31-42).
     if constexpr (OP < OP_L2I) {
-        if (p.dim == 96) return launch_fast<ROWT, OP, 96>(p, cfg);
-        if (p.dim == 128) return launch_fast<ROWT, OP, 128>(p, cfg);
-        if (p.dim >= 256 && !p.no_split) return launch_fast<ROWT, OP, 0, 4>(p, cfg);
+        if (p.dim == 96) return launch_fast<ROWT, OP, 96, 1, HIST>(p, cfg);
+        if (p.dim == 128 && !HIST) return launch_fast<ROWT, OP, 128, 1, HIST>(p, cfg);
+        if (p.dim >= 256 && !p.no_split) return launch_fast<ROWT, OP, 0, 4, HIST>(p, cfg);
     }
-    return launch_fast<ROWT, OP, 0>(p, cfg);
+    return launch_fast<ROWT, OP, 0, 1, HIST>(p, cfg);
 }
 
 }  // namespace svsb200

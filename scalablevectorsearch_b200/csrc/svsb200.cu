@@ -34,6 +34,7 @@ static int fail(const std::string& msg) {
     g_error = msg;
     return 1;
 }
+int set_error(const std::string& msg) { return fail(msg); }
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
         cudaError_t err__ = (expr);                                                            \

@@ -130,8 +130,52 @@ def lvq8_compress(data: np.ndarray, mean: np.ndarray | None = None, device: int 
     return rows, mean
 
 
+@dataclass
+class VamanaBuildParameters:
+    """``svs.VamanaBuildParameters`` (index/vamana/build_params.h; defaults lib/preprocessor.h:179-183,
+    index/vamana/index.h:1079-1095): 0 / None select the reference's defaults."""
+    alpha: float = 0.0
+    graph_max_degree: int = 32
+    window_size: int = 200
+    max_candidate_pool_size: int = 0
+    prune_to: int = 0
+    use_full_search_history: bool = True
+
+
+def build_graph(data: np.ndarray, distance: "DistanceType", parameters: VamanaBuildParameters, device: int = 0):
+    """Vamana graph construction on the GPU (``svsb200_build_vamana``; stands where ``svs.Vamana.build`` /
+    ``index::vamana::auto_build`` runs the reference's CPU builder).  Returns ``(graph uint32[n][R+1] in the
+    reference's degree-first layout, entry_point)``."""
+    data = np.ascontiguousarray(data)
+    if data.dtype not in (np.float32, np.float16) or data.ndim != 2:
+        raise TypeError("build_graph takes a 2-D float32 / float16 array")
+    if not parameters.use_full_search_history:
+        raise ValueError("the GPU builder always keeps the full search history (the reference's default)")
+    lib = _lib.lib()
+    n, R = data.shape[0], int(parameters.graph_max_degree)
+    graph = np.empty((n, R + 1), dtype=np.uint32)
+    ep = C.c_uint32()
+    _lib.check(lib.svsb200_build_vamana(
+        data.ctypes.data, _DTYPE_CODE[data.dtype], n, data.shape[1], 0, int(distance), float(parameters.alpha), R,
+        int(parameters.window_size), int(parameters.max_candidate_pool_size), int(parameters.prune_to), int(device),
+        graph.ctypes.data, C.byref(ep)))
+    return graph, int(ep.value)
+
+
 class Vamana:
     """GPU-backed static Vamana index exposing the reference's search surface."""
+
+    @classmethod
+    def build(cls, parameters: VamanaBuildParameters, data: np.ndarray, distance: "DistanceType" = None, device=0,
+              num_threads: int = 1) -> "Vamana":
+        """``svs.Vamana.build(parameters, data_loader, distance_type, num_threads)``
+        (bindings/python/src/vamana.cpp:171-240): graph construction and the resulting index, all on the GPU."""
+        distance = DistanceType.L2 if distance is None else distance
+        dev0 = device[0] if isinstance(device, (list, tuple)) else device
+        graph, ep = build_graph(data, distance, parameters, dev0)
+        self = cls.from_arrays(data, graph, ep, distance, device=device, num_threads=num_threads)
+        self.build_parameters = parameters
+        return self
 
     def __init__(self, config_path, graph_loader, data_loader, distance: DistanceType = DistanceType.L2,
                  query_type: DataType = DataType.float32, enforce_dims: bool = False, num_threads: int = 1,
