@@ -962,21 +962,20 @@ int svsb200_search_device(svsb200_index* ix, const void* d_queries, int qdtype, 
                             sc->stream);
 }
 
-// Waits for the streams of `scs`; with a cancel callback it polls the callback meanwhile and raises the device
-// flags the kernels poll per query and per hop (greedy_search.h:155, extensions.h:579).
-static int wait_all(const std::vector<Scratch*>& scs, int (*cancel)(void*), void* cancel_arg) {
+// Waits for the search kernels of `scs` (their ev_stop events); with a cancel callback it polls the callback
+// meanwhile and raises the device flags the kernels poll per query and per hop (greedy_search.h:155,
+// extensions.h:579).
+static int wait_kernels(const std::vector<Scratch*>& scs, int (*cancel)(void*), void* cancel_arg) {
+    if (!cancel) return 0;   // nothing to poll for: the stream order of the copies behind the kernels is enough
     bool raised = false;
     for (;;) {
         bool busy = false;
         for (Scratch* sc : scs) {
+            if (!sc->timed) continue;
             cudaSetDevice(sc->device);
-            if (!cancel) {
-                CUDA_TRY(cudaStreamSynchronize(sc->stream));
-                continue;
-            }
-            cudaError_t q = cudaStreamQuery(sc->stream);
+            cudaError_t q = cudaEventQuery(sc->ev_stop);
             if (q == cudaErrorNotReady) busy = true;
-            else if (q != cudaSuccess) return fail(std::string("cudaStreamQuery: ") + cudaGetErrorString(q));
+            else if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
         }
         if (!busy) return 0;
         if (!raised && cancel(cancel_arg)) {
@@ -988,6 +987,13 @@ static int wait_all(const std::vector<Scratch*>& scs, int (*cancel)(void*), void
         }
         std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
+}
+static int wait_all(const std::vector<Scratch*>& scs) {
+    for (Scratch* sc : scs) {
+        cudaSetDevice(sc->device);
+        CUDA_TRY(cudaStreamSynchronize(sc->stream));
+    }
+    return 0;
 }
 
 int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
@@ -1005,6 +1011,7 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
     const size_t qrow = ix->dim * esize(qdtype);
     std::vector<Scratch*> used;
     std::vector<Replica*> used_rep;
+    std::vector<size_t> used_lo, used_m;
     int rc = 0;
     for (size_t r = 0; r < R && rc == 0; ++r) {
         size_t lo, hi;
@@ -1025,6 +1032,9 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
         used.push_back(sc);
         used_rep.push_back(stream_ ? nullptr : rep);
         const size_t m = hi - lo;
+        used_lo.push_back(lo);
+        used_m.push_back(m);
+        sc->timed = false;
         auto step = [&]() -> int {
             CUDA_TRY(sc->q_raw.ensure(m * qrow));
             CUDA_TRY(sc->ids.ensure(m * k * size_t(id_bytes)));
@@ -1033,17 +1043,29 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
                                      cudaMemcpyHostToDevice, sc->stream));
             int rc2 = search_on_device(ix, rep, sc, sc->q_raw.ptr, qdtype, m, k, window, capacity, sc->ids.ptr, id_bytes,
                                        sc->dists.ptr, sc->stream);
-            if (rc2) return rc2;
-            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_ids) + lo * k * size_t(id_bytes), sc->ids.ptr,
-                                     m * k * size_t(id_bytes), cudaMemcpyDeviceToHost, sc->stream));
-            CUDA_TRY(cudaMemcpyAsync(out_dists + lo * k, sc->dists.ptr, m * k * sizeof(float), cudaMemcpyDeviceToHost,
-                                     sc->stream));
-            return 0;
+            return rc2;
         };
         rc = step();
     }
-    const std::string first_error = g_error;
-    int rc_wait = wait_all(used, cancel, cancel_arg);
+    std::string first_error = g_error;
+    // the kernels of every replica are in flight: poll the predicate until they finish (a copy into pageable host
+    // memory would block this thread, so the device-to-host copies are only enqueued afterwards)
+    int rc_wait = wait_kernels(used, cancel, cancel_arg);
+    for (size_t i = 0; i < used.size() && rc == 0 && rc_wait == 0; ++i) {
+        Scratch* sc = used[i];
+        if (!sc->timed) continue;
+        auto copy_out = [&]() -> int {
+            CUDA_TRY(cudaSetDevice(sc->device));
+            CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out_ids) + used_lo[i] * k * size_t(id_bytes), sc->ids.ptr,
+                                     used_m[i] * k * size_t(id_bytes), cudaMemcpyDeviceToHost, sc->stream));
+            CUDA_TRY(cudaMemcpyAsync(out_dists + used_lo[i] * k, sc->dists.ptr, used_m[i] * k * sizeof(float),
+                                     cudaMemcpyDeviceToHost, sc->stream));
+            return 0;
+        };
+        rc = copy_out();
+        if (rc) first_error = g_error;
+    }
+    if (rc_wait == 0) rc_wait = wait_all(used);
     for (size_t i = 0; i < used.size(); ++i)
         if (used_rep[i]) release(used_rep[i], used[i]);
     if (rc) {
@@ -1148,7 +1170,7 @@ int svsb200_search_sharded(svsb200_index* const* shards, size_t nshards, const v
     };
     int rc = body();
     const std::string first_error = g_error;
-    int rc_wait = wait_all(scs, nullptr, nullptr);
+    int rc_wait = wait_all(scs);
     give_back();
     if (rc) {
         g_error = first_error;
