@@ -42,6 +42,15 @@ WORKLOADS = {
                                    graph_from="c2-1Mx96-f32-L2-w128"),
     "c5s-2Mx96-f16-L2-sharded": dict(n=2_000_000, dim=96, dtype="float16", metric="l2", nq=10_000, k=10, window=128,
                                      max_degree=64, build_window=128, alpha=1.2, sharded=True),
+    # BASELINE configs[2..4] at their stated sizes; graphs from the GPU builder (svsb200_build_vamana: the reference's
+    # CPU builder needs minutes to hours at these sizes) -- both arms then search that same graph
+    "c3-1Mx768-f16-IP-w128": dict(n=1_000_000, dim=768, dtype="float16", metric="ip", nq=10_000, k=10, window=128,
+                                  max_degree=64, build_window=128, alpha=0.95, builder="gpu"),
+    "c4-10Mx96-lvq8-L2-w128": dict(n=10_000_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
+                                   max_degree=64, build_window=128, alpha=1.2, storage="lvq8", builder="gpu"),
+    "c5-100Mx96-f16-L2-sharded": dict(n=100_000_000, dim=96, dtype="float16", metric="l2", nq=100_000, k=10, window=128,
+                                      max_degree=64, build_window=128, alpha=1.2, sharded=True, builder="gpu",
+                                      per_shard_data=True),
     "tiny-100kx96-f32-L2-w128": dict(n=100_000, dim=96, dtype="float32", metric="l2", nq=10_000, k=10, window=128,
                                      max_degree=64, build_window=128, alpha=1.2),
 }
@@ -75,9 +84,23 @@ def dist_env():
 # ------------------------------------------------------------------------------------------------
 def build_graph_cached(tag, w, base, rank_builds, barrier):
     """Vamana graph from the reference's own CPU builder (oracle/_ref), cached per box under /tmp."""
-    key = hashlib.sha1(json.dumps({k: w[k] for k in ("n", "dim", "dtype", "metric", "max_degree", "build_window",
-                                                       "alpha")}, sort_keys=True).encode()).hexdigest()[:12]
+    key = hashlib.sha1(json.dumps({k: w.get(k) for k in ("n", "dim", "dtype", "metric", "max_degree", "build_window",
+                                                           "alpha", "builder")}, sort_keys=True).encode()).hexdigest()[:12]
     cache = os.path.join(os.environ.get("SVSB200_CACHE", "/tmp/svsb200_cache"), f"graph_{tag}_{key}.npy")
+    if rank_builds and not os.path.exists(cache) and w.get("builder") == "gpu":
+        from scalablevectorsearch_b200 import DistanceType, VamanaBuildParameters, build_graph
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        t1 = time.time()
+        graph, ep = build_graph(base, {"l2": DistanceType.L2, "ip": DistanceType.MIP}[w["metric"]],
+                                VamanaBuildParameters(alpha=w["alpha"], graph_max_degree=w["max_degree"],
+                                                      window_size=w["build_window"]),
+                                device=int(os.environ.get("LOCAL_RANK", 0)))
+        log(f"GPU graph build {tag} n={base.shape[0]} dim={base.shape[1]} R={w['max_degree']}: {time.time() - t1:.1f} s, "
+            f"avg degree {graph[:, 0].mean():.1f}")
+        tmp = cache + f".tmp{os.getpid()}"
+        with open(tmp, "wb") as f:
+            np.save(f, np.concatenate([np.array([[ep] + [0] * w["max_degree"]], dtype=np.uint32), graph]))
+        os.replace(tmp, cache)
     if rank_builds and not os.path.exists(cache):
         from oracle.bindings import RefLib   # checker/baseline infrastructure: builds the graph only
         if not RefLib.available():
@@ -515,10 +538,16 @@ def run_sharded(args):
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     w = WORKLOADS[args.workload]
-    base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
     lo, hi = balance(w["n"], world, rank)
-    shard = np.ascontiguousarray(base[lo:hi].astype(np.float16 if w["dtype"] == "float16" else np.float32))
-    del base
+    if w.get("per_shard_data"):
+        from scalablevectorsearch_b200.synthetic import clustered_base_block, clustered_queries
+        queries = clustered_queries(w["nq"], w["dim"], 0)
+        shard = clustered_base_block(hi - lo, w["dim"], rank)
+    else:
+        base, queries = clustered_unit_vectors(w["n"], w["nq"], w["dim"])
+        shard = base[lo:hi]
+        del base
+    shard = np.ascontiguousarray(shard.astype(np.float16 if w["dtype"] == "float16" else np.float32))
     ws = dict(w, n=hi - lo, build_share=world)
     ep, graph = build_graph_cached(f"{args.workload}_shard{rank}of{world}", ws, shard, True, lambda: None)
     barrier()

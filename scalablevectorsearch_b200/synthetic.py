@@ -30,3 +30,10 @@ def clustered_queries(nq: int, dim: int, shard: int = 0, clusters: int = 1024, s
     used to give every GPU its own batch when per-GPU work is held fixed."""
     centres = np.random.default_rng(CENTRES_SEED).standard_normal((clusters, dim), dtype=np.float32)
     return _mixture(nq, dim, centres, QUERY_SEED + shard, sigma)
+
+
+def clustered_base_block(n: int, dim: int, block: int, clusters: int = 1024, sigma: float = 0.35) -> np.ndarray:
+    """Base-vector block number ``block`` of the same law: sharded datasets are defined shard by shard (shard s
+    of a G-way sharded index is block s), so every rank generates only its own rows."""
+    centres = np.random.default_rng(CENTRES_SEED).standard_normal((clusters, dim), dtype=np.float32)
+    return _mixture(n, dim, centres, BASE_SEED + 7919 * (block + 1), sigma)
