@@ -203,6 +203,22 @@ int svsb200_build_vamana(
     float alpha, size_t graph_max_degree, size_t window_size, size_t max_candidate_pool_size,
     size_t prune_to, int device, uint32_t* graph_rows_out, uint32_t* entry_point_out);
 
+/* Exact exhaustive (flat) search on the tensor cores.  Replaces: svs::Flat / FlatIndex::search
+ * (include/svs/index/flat/flat.h:159,421-465): top-k of every query against all `n` base vectors inside `index`.
+ * A query-tile x base-tile fp16 GEMM (tcgen05 / TMEM, operands staged by bulk copies) selects candidates, the
+ * candidates are re-scored with the graph search's own bit-exact distance code, and an error bound on the fp16
+ * products proves per query that no other vector can belong to the top k; queries that fail the proof are
+ * re-run by the exact scan.  The result therefore always equals svsb200_exhaustive_device bit for bit (ids and
+ * distances; ties by id).  float32/float16 data and queries, L2 and MIP, k <= 25; other shapes take the scan.
+ * `fallback_queries` (optional) receives how many queries needed the scan. */
+int svsb200_flat_search_device(
+    svsb200_index* index, const void* d_queries, int qdtype, size_t nq, size_t k,
+    uint64_t* d_out_ids, float* d_out_dists, void* stream, uint32_t* fallback_queries);
+/* The same with HOST buffers (blocking). */
+int svsb200_flat_search(
+    svsb200_index* index, const void* queries, int qdtype, size_t nq, size_t k,
+    uint64_t* out_ids, float* out_dists);
+
 /* Exhaustive search used by the harness for ground truth (replaces svs::Flat /
  * index/flat/flat.h:159 for recall measurement only): top-k of every query against all
  * `n` base vectors already on the device inside `index`. Distances use the same exact

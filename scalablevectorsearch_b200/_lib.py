@@ -21,7 +21,7 @@ SYMBOLS = [
     "svsb200_get_counters", "svsb200_get_fetched", "svsb200_last_kernel_ms", "svsb200_launch_count", "svsb200_set_option", "svsb200_get_option",
     "svsb200_merge_topk_device", "svsb200_exhaustive_device", "svsb200_lvq8_row_stride", "svsb200_lvq8_compress",
     "svsb200_index_create_multi", "svsb200_index_num_devices", "svsb200_search_cancellable", "svsb200_set_id_offset",
-    "svsb200_search_sharded", "svsb200_build_vamana",
+    "svsb200_search_sharded", "svsb200_build_vamana", "svsb200_flat_search_device", "svsb200_flat_search",
 ]
 
 _lib = None
@@ -70,6 +70,8 @@ def lib() -> C.CDLL:
     l.svsb200_search_cancellable.argtypes = [vp, vp, i32, sz, sz, sz, sz, i32, vp, i32, vp, vp, CANCEL_FN, vp]
     l.svsb200_set_id_offset.argtypes = [vp, C.c_uint64]
     l.svsb200_search_sharded.argtypes = [C.POINTER(vp), sz, vp, i32, sz, sz, sz, sz, vp, vp]
+    l.svsb200_flat_search_device.argtypes = [vp, vp, i32, sz, sz, vp, vp, vp, C.POINTER(u32)]
+    l.svsb200_flat_search.argtypes = [vp, vp, i32, sz, sz, vp, vp]
     l.svsb200_build_vamana.argtypes = [vp, i32, sz, sz, sz, i32, C.c_float, sz, sz, sz, sz, i32, vp, C.POINTER(u32)]
     _lib = l
     return l

@@ -14,6 +14,7 @@
 // No CPU fallback lives here: every entry point either runs CUDA kernels on an sm_100 device or fails.
 #include "common.cuh"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <cmath>
@@ -75,6 +76,10 @@ struct Scratch {
     DeviceBuffer<unsigned char> q_raw, q_codes, ids;
     DeviceBuffer<float> q_f32, q_aux, dists;
     DeviceBuffer<uint32_t> hops, evals, fetched;
+    DeviceBuffer<unsigned char> flat_a, flat_q2;       // tensor-core flat search: query tiles, gathered queries
+    DeviceBuffer<float> flat_qnorm, flat_ckey, flat_d2;
+    DeviceBuffer<uint32_t> flat_cid, flat_unv;         // candidates, unverified list (+ its counter in slot 0)
+    DeviceBuffer<uint64_t> flat_i2;
     DeviceBuffer<uint64_t> gather_ids, merged_ids;     // sharded search (on the merging device)
     DeviceBuffer<float> gather_dists, merged_dists;
     unsigned int* d_counter = nullptr;
@@ -88,6 +93,8 @@ struct Scratch {
         q_raw.release(); q_codes.release(); ids.release(); q_f32.release(); q_aux.release(); dists.release();
         hops.release(); evals.release(); fetched.release();
         gather_ids.release(); merged_ids.release(); gather_dists.release(); merged_dists.release();
+        flat_a.release(); flat_q2.release(); flat_qnorm.release(); flat_ckey.release(); flat_d2.release();
+        flat_cid.release(); flat_unv.release(); flat_i2.release();
         if (d_counter) cudaFree(d_counter);
         if (d_cancel) cudaFree(d_cancel);
         if (ev_start) cudaEventDestroy(ev_start);
@@ -106,6 +113,10 @@ struct Replica {
     uint32_t* d_graph = nullptr;
     uint16_t* d_ref_degree = nullptr;
     float* d_mean = nullptr;          // LVQ-8: dataset mean
+    // tensor-core flat search: the base vectors as fp16 UMMA tiles + per-row bias, built on first use
+    void* flat_b = nullptr;
+    float* flat_bias = nullptr;
+    unsigned int* flat_xmax = nullptr;
     std::mutex mu;
     std::vector<Scratch*> idle;                      // pool for the blocking API
     std::map<cudaStream_t, Scratch*> by_stream;      // one per caller stream for the enqueue-only API
@@ -117,6 +128,9 @@ struct Replica {
         if (d_graph) cudaFree(d_graph);
         if (d_ref_degree) cudaFree(d_ref_degree);
         if (d_mean) cudaFree(d_mean);
+        if (flat_b) cudaFree(flat_b);
+        if (flat_bias) cudaFree(flat_bias);
+        if (flat_xmax) cudaFree(flat_xmax);
     }
 };
 
@@ -1257,6 +1271,137 @@ int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* 
     if (d_rows) cudaFree(d_rows);
     CUDA_TRY(err);
     return 0;
+}
+
+// Shared body of the tensor-core flat search: device buffers in, device buffers out, enqueued on sc->stream except
+// for one synchronisation (the count of queries that need the exact-scan fallback).
+static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const void* d_queries, int qdtype, size_t nq, size_t k,
+                          uint64_t* d_out_ids, float* d_out_dists, uint32_t* fallback_queries) {
+    if (fallback_queries) *fallback_queries = 0;
+    if (nq == 0) return 0;
+    cudaStream_t stream = sc->stream;
+    const bool gemm_ok = ix->storage == SVSB200_PLAIN && (ix->dtype == SVSB200_F32 || ix->dtype == SVSB200_F16) &&
+                         ix->metric != SVSB200_COSINE && (qdtype == SVSB200_F32 || qdtype == SVSB200_F16) &&
+                         k + 8 <= flat_kc() && ix->n >= 512;
+    if (!gemm_ok) {   // shapes outside the GEMM path: the exact scan
+        if (fallback_queries) *fallback_queries = uint32_t(nq);
+        return search_on_device(ix, rep, sc, d_queries, qdtype, nq, k, k, k, d_out_ids, 8, d_out_dists, stream, true);
+    }
+    const uint32_t n = uint32_t(ix->n), dim = uint32_t(ix->dim);
+    const uint32_t KB = (dim + 31) / 32, ntiles = (n + 255) / 256, mtiles = uint32_t((nq + 127) / 128);
+    const int l2 = ix->metric == SVSB200_L2;
+    {   // base tiles, once per replica
+        std::lock_guard<std::mutex> lock(rep->mu);
+        if (!rep->flat_b) {
+            CUDA_TRY(cudaMalloc(&rep->flat_b, size_t(ntiles) * 256 * KB * 32 * 2));
+            CUDA_TRY(cudaMalloc(&rep->flat_bias, size_t(ntiles) * 256 * 4));
+            CUDA_TRY(cudaMalloc(&rep->flat_xmax, 4));
+            CUDA_TRY(cudaMemsetAsync(rep->flat_xmax, 0, 4, stream));
+            CUDA_TRY(flat_tile_rows(ix->dtype, rep->d_vectors, ix->row_stride, n, dim, 256, 1.0f, l2, rep->flat_b, rep->flat_bias,
+                                    nullptr, rep->flat_xmax, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+        }
+    }
+    uint32_t nsplit = (2u * uint32_t(rep->sm_count) + mtiles - 1) / mtiles;
+    nsplit = std::max(1u, std::min(std::min(nsplit, 15u), ntiles));
+    const size_t qrow = size_t(dim) * esize(qdtype);
+    CUDA_TRY(sc->flat_a.ensure(size_t(mtiles) * 128 * KB * 32 * 2));
+    CUDA_TRY(sc->flat_qnorm.ensure(size_t(mtiles) * 128));
+    CUDA_TRY(sc->flat_ckey.ensure(size_t(mtiles) * 128 * nsplit * flat_kc()));
+    CUDA_TRY(sc->flat_cid.ensure(size_t(mtiles) * 128 * nsplit * flat_kc()));
+    CUDA_TRY(sc->flat_unv.ensure(nq + 1));
+    CUDA_TRY(flat_tile_rows(qdtype, d_queries, uint32_t(qrow), uint32_t(nq), dim, 128, 1.0f, 0, sc->flat_a.ptr, nullptr,
+                            sc->flat_qnorm.ptr, nullptr, stream));
+    CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, nsplit, l2 ? -2.0f : -1.0f,
+                            sc->flat_ckey.ptr, sc->flat_cid.ptr, stream));
+    // exact re-scoring with the search path's distance code: prepared queries as for a search
+    const uint32_t qstride = uint32_t(round_up(ix->dim, 16));
+    CUDA_TRY(sc->q_f32.ensure(nq * qstride));
+    CUDA_TRY(sc->q_codes.ensure(nq * qstride));
+    CUDA_TRY(sc->q_aux.ensure(nq * 2));
+    cudaError_t err = qdtype == SVSB200_F32
+        ? launch_prepare<SVSB200_F32>(d_queries, uint32_t(nq), dim, qstride, PREP_FLOAT, ix->metric, ix->dtype, ix->scale, ix->bias,
+                                      rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream)
+        : launch_prepare<SVSB200_F16>(d_queries, uint32_t(nq), dim, qstride, PREP_FLOAT, ix->metric, ix->dtype, ix->scale, ix->bias,
+                                      rep->d_mean, sc->q_f32.ptr, sc->q_codes.ptr, sc->q_aux.ptr, stream);
+    CUDA_TRY(err);
+    SearchParams p{};
+    p.vectors = rep->d_vectors;
+    p.n = n;
+    p.dim = dim;
+    p.row_stride = ix->row_stride;
+    p.greater = !l2;
+    p.scale = 1.f;
+    p.qf = sc->q_f32.ptr;
+    p.qaux = sc->q_aux.ptr;
+    p.qstride = qstride;
+    p.nq = uint32_t(nq);
+    p.k = uint32_t(k);
+    CUDA_TRY(cudaMemsetAsync(sc->flat_unv.ptr, 0, 4, stream));
+    CUDA_TRY(flat_rescore(ix->dtype, l2 ? OP_L2F : OP_IPF, p, sc->flat_ckey.ptr, sc->flat_cid.ptr, nsplit, uint32_t(nq), uint32_t(k),
+                          sc->flat_qnorm.ptr, rep->flat_xmax, d_out_ids, d_out_dists, sc->flat_unv.ptr + 1, sc->flat_unv.ptr, stream));
+    // queries whose bound did not verify: exact scan, results scattered over the rescored rows
+    uint32_t nunv = 0;
+    CUDA_TRY(cudaMemcpyAsync(&nunv, sc->flat_unv.ptr, 4, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if (fallback_queries) *fallback_queries = nunv;
+    if (nunv) {
+        CUDA_TRY(sc->flat_q2.ensure(size_t(nunv) * qrow));
+        CUDA_TRY(sc->flat_i2.ensure(size_t(nunv) * k));
+        CUDA_TRY(sc->flat_d2.ensure(size_t(nunv) * k));
+        CUDA_TRY(flat_move_rows(d_queries, sc->flat_q2.ptr, sc->flat_unv.ptr + 1, sc->flat_unv.ptr, nunv, uint32_t(qrow), 0, stream));
+        int rc = search_on_device(ix, rep, sc, sc->flat_q2.ptr, qdtype, nunv, k, k, k, sc->flat_i2.ptr, 8, sc->flat_d2.ptr, stream, true);
+        if (rc) return rc;
+        CUDA_TRY(flat_move_rows(sc->flat_i2.ptr, d_out_ids, sc->flat_unv.ptr + 1, sc->flat_unv.ptr, nunv, uint32_t(k * 8), 1, stream));
+        CUDA_TRY(flat_move_rows(sc->flat_d2.ptr, d_out_dists, sc->flat_unv.ptr + 1, sc->flat_unv.ptr, nunv, uint32_t(k * 4), 1, stream));
+    }
+    return 0;
+}
+
+int svsb200_flat_search_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, uint64_t* d_out_ids,
+                               float* d_out_dists, void* stream_, uint32_t* fallback_queries) {
+    if (!ix) return fail("svsb200_flat_search_device: NULL index");
+    if (nq && (!d_queries || !d_out_ids || !d_out_dists)) return fail("svsb200_flat_search_device: NULL buffer");
+    if (k == 0 || k > 1024) return fail("svsb200_flat_search_device: k must be in [1, 1024]");
+    if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
+    if (ix->reps.size() != 1) return fail("svsb200_flat_search_device: the index must live on exactly one device");
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    Scratch* sc = scratch_for_stream(rep, static_cast<cudaStream_t>(stream_), &err);
+    if (!sc) return fail(err);
+    return flat_on_device(ix, rep, sc, d_queries, qdtype, nq, k, d_out_ids, d_out_dists, fallback_queries);
+}
+
+int svsb200_flat_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, uint64_t* out_ids,
+                        float* out_dists) {
+    if (!ix) return fail("svsb200_flat_search: NULL index");
+    if (nq == 0) return 0;
+    if (!queries || !out_ids || !out_dists) return fail("svsb200_flat_search: NULL buffer");
+    if (k == 0 || k > 1024) return fail("svsb200_flat_search: k must be in [1, 1024]");
+    if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    Scratch* sc = acquire(rep, &err);
+    if (!sc) return fail(err);
+    auto body = [&]() -> int {
+        const size_t qbytes = nq * ix->dim * esize(qdtype);
+        CUDA_TRY(sc->q_raw.ensure(qbytes));
+        CUDA_TRY(sc->ids.ensure(nq * k * 8));
+        CUDA_TRY(sc->dists.ensure(nq * k));
+        CUDA_TRY(cudaMemcpyAsync(sc->q_raw.ptr, queries, qbytes, cudaMemcpyHostToDevice, sc->stream));
+        int rc = flat_on_device(ix, rep, sc, sc->q_raw.ptr, qdtype, nq, k, reinterpret_cast<uint64_t*>(sc->ids.ptr), sc->dists.ptr,
+                                nullptr);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(out_ids, sc->ids.ptr, nq * k * 8, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_dists, sc->dists.ptr, nq * k * 4, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaStreamSynchronize(sc->stream));
+        return 0;
+    };
+    int rc = body();
+    release(rep, sc);
+    return rc;
 }
 
 int svsb200_exhaustive_device(svsb200_index* ix, const void* d_queries, int qdtype, size_t nq, size_t k, uint64_t* d_out_ids,

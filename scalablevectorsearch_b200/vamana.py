@@ -330,6 +330,28 @@ class Vamana:
         _lib.check(self._lib.svsb200_exhaustive_device(self._h, d_queries, _DTYPE_CODE[np.dtype(qdtype)], nq,
                                                        int(n_neighbors), d_ids, d_dists, stream or None))
 
+    def flat_search(self, queries: np.ndarray, n_neighbors: int):
+        """Exact top-k of every query over ALL base vectors -- what ``svs.Flat(...).search`` computes
+        (index/flat/flat.h:421-465) -- on the tensor cores, with the graph search's bit-exact distances
+        (``svsb200_flat_search``)."""
+        q = np.ascontiguousarray(queries)
+        if q.ndim != 2 or q.shape[1] != self.dimensions:
+            raise ValueError("queries must be [nq, dim]")
+        nq, k = q.shape[0], int(n_neighbors)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        _lib.check(self._lib.svsb200_flat_search(self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k, ids.ctypes.data,
+                                                 dists.ctypes.data))
+        return ids, dists
+
+    def flat_search_device(self, d_queries: int, qdtype: np.dtype, nq: int, n_neighbors: int, d_ids: int, d_dists: int,
+                           stream: int = 0) -> int:
+        """Device-buffer form; returns how many queries needed the exact-scan fallback."""
+        fb = C.c_uint32()
+        _lib.check(self._lib.svsb200_flat_search_device(self._h, d_queries, _DTYPE_CODE[np.dtype(qdtype)], nq,
+                                                        int(n_neighbors), d_ids, d_dists, stream or None, C.byref(fb)))
+        return int(fb.value)
+
     # ---- instrumentation ---------------------------------------------------------------
     def set_counting(self, enabled: bool):
         _lib.check(self._lib.svsb200_set_counting(self._h, int(enabled)))
