@@ -74,6 +74,20 @@ int svsb200_index_create_multi(
     const uint32_t* graph_rows, size_t graph_row_len, uint32_t entry_point, int metric,
     int storage, const float* aux, const int* devices, size_t ndevices, svsb200_index** out);
 
+/* Replaces: index::vamana::auto_assemble(config_path, GraphLoader, VectorDataLoader, distance, threads)
+ * (include/svs/index/vamana/index.h:1022-1050) for uncompressed data: the VamanaIndexParameters TOML
+ * (`svs_config.toml` inside `config_path`, or the file itself; index.h:53-178) is parsed here (entry point, saved
+ * search parameters -> svsb200_get_option "config_search_window_size" / "config_search_buffer_capacity"), and
+ * the native v1 `.svs` containers (core/io/native.h:315-345; `graph_0.svs` / `data_0.svs` inside a directory) or
+ * `[fibh]vecs` files (core/io/vecs.h:137-273) are streamed through pinned staging buffers straight into HBM --
+ * no host copy of the dataset is made.  `expected_dims` != 0 is VectorDataLoader's `dims` check. */
+int svsb200_index_assemble(
+    const char* config_path, const char* graph_path, const char* data_path, int dtype, size_t expected_dims,
+    int metric, const int* devices, size_t ndevices, svsb200_index** out);
+/* The TOML subset reader behind it (tables, dotted table names, integers, floats, booleans, strings): copies the
+ * raw text of `table.key` into `out`. */
+int svsb200_toml_get(const char* path, const char* dotted_key, char* out, size_t capacity);
+
 int svsb200_index_destroy(svsb200_index* index);
 
 /* Introspection used by the host-side mirror (size()/dimensions()/get_graph_max_degree,

@@ -25,6 +25,8 @@
 #include <thread>
 #include <vector>
 
+#include <sys/stat.h>
+
 namespace svsb200 {
 
 static thread_local std::string g_error;
@@ -146,6 +148,7 @@ struct svsb200_index {
     uint32_t lvq_const_offset = 0;
     size_t device_bytes = 0;          // per replica
     uint64_t id_offset = 0;           // added to every 64-bit output id (shard of a larger index)
+    long cfg_window = 0, cfg_capacity = 0, cfg_visited = 0;   // search parameters of the TOML an index was assembled from
     std::vector<std::unique_ptr<Replica>> reps;
     int counting = 0;
     // options
@@ -682,6 +685,309 @@ int svsb200_index_create(const void* vectors, int dtype, size_t n, size_t dim, s
                                       metric, storage, aux, &device, 1, out);
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// Assembling an index from files, streamed straight into HBM.  Replaces
+// index::vamana::auto_assemble (index/vamana/index.h:1022-1050) + the native / vecs readers
+// (core/io/native.h:315-345, core/io/vecs.h:137-273) + the TOML load of VamanaIndexParameters
+// (index/vamana/index.h:53-178, lib/saveload/load.h:829-878).
+// -----------------------------------------------------------------------------------------------------------------
+namespace {
+
+// A TOML subset sufficient for the reference's saved configurations: comments, [tables] with dotted names,
+// [[arrays of tables]] (skipped), key = value with integers, floats, booleans, 'literal' / "basic" strings,
+// dates as bare tokens.  Returns "table.key" -> raw value text (strings unquoted).
+bool parse_toml_subset(const std::string& text, std::map<std::string, std::string>& out, std::string& err) {
+    std::string table;
+    bool skip = false;
+    size_t line_no = 0, pos = 0;
+    while (pos <= text.size()) {
+        size_t eol = text.find('\n', pos);
+        if (eol == std::string::npos) eol = text.size();
+        std::string line = text.substr(pos, eol - pos);
+        pos = eol + 1;
+        ++line_no;
+        // strip comments outside strings
+        bool in_s = false, in_d = false;
+        for (size_t i = 0; i < line.size(); ++i) {
+            const char c = line[i];
+            if (c == '\'' && !in_d) in_s = !in_s;
+            else if (c == '"' && !in_s && (i == 0 || line[i - 1] != '\\')) in_d = !in_d;
+            else if (c == '#' && !in_s && !in_d) {
+                line.resize(i);
+                break;
+            }
+        }
+        auto trim = [](std::string& v) {
+            const size_t b = v.find_first_not_of(" \t\r");
+            if (b == std::string::npos) {
+                v.clear();
+                return;
+            }
+            v = v.substr(b, v.find_last_not_of(" \t\r") - b + 1);
+        };
+        trim(line);
+        if (line.empty()) continue;
+        if (line[0] == '[') {
+            if (line.size() > 1 && line[1] == '[') {   // array of tables: not needed for index parameters
+                skip = true;
+                continue;
+            }
+            const size_t close = line.find(']');
+            if (close == std::string::npos) {
+                err = "line " + std::to_string(line_no) + ": unterminated table header";
+                return false;
+            }
+            table = line.substr(1, close - 1);
+            trim(table);
+            skip = false;
+            continue;
+        }
+        if (skip) continue;
+        const size_t eq = line.find('=');
+        if (eq == std::string::npos) {
+            err = "line " + std::to_string(line_no) + ": expected key = value";
+            return false;
+        }
+        std::string key = line.substr(0, eq), value = line.substr(eq + 1);
+        trim(key);
+        trim(value);
+        if (key.size() >= 2 && (key.front() == '"' || key.front() == '\'')) key = key.substr(1, key.size() - 2);
+        if (value.size() >= 2 && (value.front() == '\'' || value.front() == '"') && value.back() == value.front())
+            value = value.substr(1, value.size() - 2);
+        if (key.empty() || value.empty()) {
+            err = "line " + std::to_string(line_no) + ": empty key or value";
+            return false;
+        }
+        out[table.empty() ? key : table + "." + key] = value;
+    }
+    return true;
+}
+
+struct RowFile {
+    FILE* f = nullptr;
+    size_t n = 0, dim = 0, esize = 0;
+    size_t row_prefix = 0;     // bytes in front of every row (vecs formats: the int32 dimension)
+    ~RowFile() {
+        if (f) fclose(f);
+    }
+};
+
+std::string resolve(const std::string& path, const char* inside) {
+    struct stat st;
+    if (stat(path.c_str(), &st) == 0 && S_ISDIR(st.st_mode)) return path + "/" + inside;
+    return path;
+}
+
+// Opens a native v1 .svs container or a [fibh]vecs file; `esize` is the element size the caller expects.
+int open_rows(const std::string& path, size_t esize, RowFile& rf) {
+    rf.f = fopen(path.c_str(), "rb");
+    if (!rf.f) return fail("cannot open " + path);
+    rf.esize = esize;
+    const size_t dot = path.rfind('.');
+    const std::string ext = dot == std::string::npos ? "" : path.substr(dot);
+    fseek(rf.f, 0, SEEK_END);
+    const size_t bytes = size_t(ftell(rf.f));
+    fseek(rf.f, 0, SEEK_SET);
+    if (ext == ".fvecs" || ext == ".ivecs" || ext == ".bvecs" || ext == ".hvecs") {
+        int32_t d = 0;
+        if (fread(&d, 4, 1, rf.f) != 1 || d <= 0) return fail(path + ": empty or malformed vecs file");
+        rf.dim = size_t(d);
+        rf.row_prefix = 4;
+        const size_t row = 4 + rf.dim * esize;
+        if (bytes % row) return fail(path + ": size is not a multiple of the row size");
+        rf.n = bytes / row;
+        fseek(rf.f, 0, SEEK_SET);
+        return 0;
+    }
+    unsigned char header[1024];
+    if (fread(header, 1, 1024, rf.f) != 1024) return fail(path + ": truncated header");
+    uint64_t magic, n, dims;
+    memcpy(&magic, header, 8);
+    memcpy(&n, header + 24, 8);
+    memcpy(&dims, header + 32, 8);
+    if (magic != 0xcad4a6b2579980feull) return fail(path + ": not a native v1 .svs file (bad magic)");
+    if (bytes < 1024 + n * dims * esize) return fail(path + ": truncated body");
+    rf.n = n;
+    rf.dim = dims;
+    return 0;
+}
+
+// Streams the rows of `rf` through two pinned staging buffers: while chunk i is copied host->device (asynchronously,
+// strided into the padded HBM rows), chunk i+1 is read from the file.  `sink(dev_chunk_rows_ptr?, ...)` is not needed:
+// rows land at dst + row * dst_stride.
+int stream_rows_to_device(RowFile& rf, char* dst, size_t dst_stride, cudaStream_t stream) {
+    const size_t src_row = rf.row_prefix + rf.dim * rf.esize;
+    const size_t chunk_rows = std::max<size_t>(1, (size_t(32) << 20) / src_row);
+    char* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    int rc = 0;
+    for (int i = 0; i < 2 && rc == 0; ++i) {
+        if (cudaMallocHost(&pinned[i], chunk_rows * src_row) != cudaSuccess || cudaEventCreate(&done[i]) != cudaSuccess)
+            rc = fail("pinned staging buffer allocation failed");
+    }
+    for (size_t r0 = 0, c = 0; r0 < rf.n && rc == 0; r0 += chunk_rows, ++c) {
+        const int b = int(c & 1);
+        const size_t rows = std::min(chunk_rows, rf.n - r0);
+        if (c >= 2 && cudaEventSynchronize(done[b]) != cudaSuccess) rc = fail("cudaEventSynchronize failed");
+        if (rc == 0 && fread(pinned[b], src_row, rows, rf.f) != rows) rc = fail("short read");
+        if (rc == 0 &&
+            cudaMemcpy2DAsync(dst + r0 * dst_stride, dst_stride, pinned[b] + rf.row_prefix, src_row, rf.dim * rf.esize, rows,
+                              cudaMemcpyHostToDevice, stream) != cudaSuccess)
+            rc = fail("cudaMemcpy2DAsync failed");
+        if (rc == 0) cudaEventRecord(done[b], stream);
+    }
+    if (cudaStreamSynchronize(stream) != cudaSuccess && rc == 0) rc = fail("stream synchronisation failed");
+    for (int i = 0; i < 2; ++i) {
+        if (pinned[i]) cudaFreeHost(pinned[i]);
+        if (done[i]) cudaEventDestroy(done[i]);
+    }
+    return rc;
+}
+
+}  // namespace
+
+int svsb200_toml_get(const char* path, const char* dotted_key, char* out, size_t capacity) {
+    if (!path || !dotted_key || !out || capacity == 0) return fail("svsb200_toml_get: NULL argument");
+    FILE* f = fopen(path, "rb");
+    if (!f) return fail(std::string("cannot open ") + path);
+    std::string text;
+    char buf[4096];
+    size_t got;
+    while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+    fclose(f);
+    std::map<std::string, std::string> cfg;
+    std::string err;
+    if (!parse_toml_subset(text, cfg, err)) return fail(std::string(path) + ": " + err);
+    auto it = cfg.find(dotted_key);
+    if (it == cfg.end()) return fail(std::string(path) + ": no key " + dotted_key);
+    if (it->second.size() + 1 > capacity) return fail("svsb200_toml_get: value does not fit");
+    memcpy(out, it->second.c_str(), it->second.size() + 1);
+    return 0;
+}
+
+int svsb200_index_assemble(const char* config_path, const char* graph_path, const char* data_path, int dtype,
+                           size_t expected_dims, int metric, const int* devices, size_t ndevices, svsb200_index** out) {
+    if (!out) return fail("svsb200_index_assemble: out is NULL");
+    *out = nullptr;
+    if (!config_path || !graph_path || !data_path) return fail("svsb200_index_assemble: NULL path");
+    if (!devices || ndevices == 0) return fail("svsb200_index_assemble: empty device list");
+    if (dtype < SVSB200_F32 || dtype > SVSB200_U8) return fail("svsb200_index_assemble: bad dtype");
+    if (metric < SVSB200_L2 || metric > SVSB200_COSINE) return fail("svsb200_index_assemble: bad metric");
+    // ---- VamanaIndexParameters from TOML ----
+    const std::string cfg_file = resolve(config_path, "svs_config.toml");
+    std::map<std::string, std::string> cfg;
+    {
+        FILE* f = fopen(cfg_file.c_str(), "rb");
+        if (!f) return fail("cannot open " + cfg_file);
+        std::string text;
+        char buf[4096];
+        size_t got;
+        while ((got = fread(buf, 1, sizeof(buf), f)) > 0) text.append(buf, got);
+        fclose(f);
+        std::string err;
+        if (!parse_toml_subset(text, cfg, err)) return fail(cfg_file + ": " + err);
+    }
+    auto cfg_long = [&](const char* key, long dflt) {
+        auto it = cfg.find(key);
+        if (it == cfg.end()) return dflt;
+        if (it->second == "true") return 1l;
+        if (it->second == "false") return 0l;
+        return strtol(it->second.c_str(), nullptr, 10);
+    };
+    if (cfg.find("object.entry_point") == cfg.end()) return fail(cfg_file + ": no entry_point in [object]");
+    const long entry_point = cfg_long("object.entry_point", 0);
+    // ---- files ----
+    RowFile data, graph;
+    int rc = open_rows(resolve(data_path, "data_0.svs"), esize(dtype), data);
+    if (rc) return rc;
+    rc = open_rows(resolve(graph_path, "graph_0.svs"), 4, graph);
+    if (rc) return rc;
+    if (expected_dims && data.dim != expected_dims)
+        return fail("svsb200_index_assemble: the data file holds " + std::to_string(data.dim) + "-dimensional vectors, " +
+                    std::to_string(expected_dims) + " expected");
+    if (graph.n != data.n) return fail("Wrong sizes!");   // index/vamana/index.h:417-419
+    const size_t n = data.n, dim = data.dim, graph_row_len = graph.dim;
+    if (n == 0 || dim == 0) return fail("svsb200_index_assemble: empty dataset");
+    if (n >= (size_t(1) << 31)) return fail("svsb200_index_assemble: more than 2^31-1 vectors per index");
+    if (graph_row_len < 2 || graph_row_len > 65536) return fail("svsb200_index_assemble: bad graph row length");
+    if (entry_point < 0 || size_t(entry_point) >= n) return fail("svsb200_index_assemble: entry point out of range");
+    const int ndev = svsb200_device_count();
+    if (ndev == 0) return fail("svsb200_index_assemble: no CUDA device (there is no CPU fallback)");
+
+    std::unique_ptr<svsb200_index> ix(new svsb200_index());
+    ix->dtype = dtype;
+    ix->metric = metric;
+    ix->storage = SVSB200_PLAIN;
+    ix->n = n;
+    ix->dim = dim;
+    ix->max_degree = graph_row_len - 1;
+    ix->entry_point = uint32_t(entry_point);
+    ix->row_stride = uint32_t(round_up(dim * esize(dtype), 16));
+    ix->gstride = uint32_t(round_up(ix->max_degree, ix->max_degree <= 32u * kFastMaxGW ? 32 : 4));
+    ix->cfg_window = cfg_long("object.search_parameters.search_window_size", 0);
+    ix->cfg_capacity = cfg_long("object.search_parameters.search_buffer_capacity", 0);
+    ix->cfg_visited = cfg_long("object.search_parameters.search_buffer_visited_set", 0);
+
+    for (size_t r = 0; r < ndevices; ++r) {
+        const int device = devices[r];
+        if (device < 0 || device >= ndev) return fail("svsb200_index_assemble: bad device ordinal");
+        cudaDeviceProp prop;
+        CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10 || prop.minor != 0)
+            return fail("svsb200_index_assemble: device is not sm_100 (this binary holds sm_100a code only)");
+        std::unique_ptr<Replica> rep(new Replica());
+        rep->device = device;
+        rep->sm_count = prop.multiProcessorCount;
+        if (r > 0) {
+            rc = clone_replica(ix.get(), ix->reps[0].get(), rep.get());
+            if (rc) return rc;
+            ix->reps.push_back(std::move(rep));
+            continue;
+        }
+        CUDA_TRY(cudaSetDevice(device));
+        cudaStream_t stream;
+        CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        const size_t vbytes = n * size_t(ix->row_stride), gbytes = n * size_t(ix->gstride) * 4;
+        uint32_t* d_src = nullptr;
+        int* d_bad = nullptr;
+        auto body = [&]() -> int {
+            CUDA_TRY(cudaMalloc(&rep->d_vectors, vbytes));
+            CUDA_TRY(cudaMalloc(&rep->d_graph, gbytes));
+            CUDA_TRY(cudaMalloc(&rep->d_ref_degree, n * 2));
+            ix->device_bytes = vbytes + gbytes + n * 2;
+            CUDA_TRY(cudaMemsetAsync(rep->d_vectors, 0, vbytes, stream));
+            int rc2 = stream_rows_to_device(data, static_cast<char*>(rep->d_vectors), ix->row_stride, stream);
+            if (rc2) return rc2;
+            // the graph: streamed into a device staging area, then repacked (degree word dropped, rows padded)
+            CUDA_TRY(cudaMalloc(&d_src, n * graph_row_len * 4));
+            CUDA_TRY(cudaMalloc(&d_bad, 4));
+            CUDA_TRY(cudaMemsetAsync(d_bad, 0, 4, stream));
+            rc2 = stream_rows_to_device(graph, reinterpret_cast<char*>(d_src), graph_row_len * 4, stream);
+            if (rc2) return rc2;
+            const int warps = 8;
+            repack_graph_kernel<<<unsigned((n + warps - 1) / warps), warps * 32, 0, stream>>>(
+                d_src, graph_row_len, uint32_t(n), rep->d_graph, ix->gstride, rep->d_ref_degree, d_bad);
+            count_launch();
+            CUDA_TRY(cudaGetLastError());
+            int bad = 0;
+            CUDA_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, stream));
+            CUDA_TRY(cudaStreamSynchronize(stream));
+            if (bad)
+                return fail(bad == 1 ? "svsb200_index_assemble: adjacency row with degree > max_degree"
+                                     : "svsb200_index_assemble: neighbour id out of range");
+            return 0;
+        };
+        rc = body();
+        if (d_src) cudaFree(d_src);
+        if (d_bad) cudaFree(d_bad);
+        cudaStreamDestroy(stream);
+        if (rc) return rc;
+        ix->reps.push_back(std::move(rep));
+    }
+    *out = ix.release();
+    return 0;
+}
+
 int svsb200_index_destroy(svsb200_index* ix) {
     delete ix;   // Replica / Scratch destructors release the device memory
     return 0;
@@ -748,6 +1054,10 @@ int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
     else if (key == "rows_in_flight") *value = ix->rows_in_flight;
     else if (key == "visited_filter_slots") *value = ix->filter_slots;
     else if (key == "generic_kernel") *value = ix->generic_kernel;
+    else if (key == "config_search_window_size") *value = ix->cfg_window;
+    else if (key == "config_search_buffer_capacity") *value = ix->cfg_capacity;
+    else if (key == "config_search_buffer_visited_set") *value = ix->cfg_visited;
+    else if (key == "entry_point") *value = long(ix->entry_point);
     else if (key == "streams") {         // scratch sets (= streams) created so far over all replicas
         long c = 0;
         for (auto& rep : ix->reps) {

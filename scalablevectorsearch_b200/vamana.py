@@ -17,7 +17,6 @@ from __future__ import annotations
 import ctypes as C
 import enum
 import os
-import re
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -102,16 +101,19 @@ class GraphLoader:
         return io.read_graph(path)
 
 
+def toml_get(path: str, dotted_key: str) -> str:
+    """Raw text of ``table.key`` in a TOML file, read by the library's own subset parser (``svsb200_toml_get``)."""
+    buf = C.create_string_buffer(4096)
+    _lib.check(_lib.lib().svsb200_toml_get(os.fsencode(path), dotted_key.encode(), buf, len(buf)))
+    return buf.value.decode()
+
+
 def _read_entry_point(config_path: str) -> int:
     """``entry_point`` of a ``vamana_index_parameters`` TOML (index/vamana/index.h:53-178)."""
     path = config_path
     if os.path.isdir(path):
         path = os.path.join(path, "svs_config.toml")
-    with open(path) as f:
-        m = re.search(r"^\s*entry_point\s*=\s*(\d+)", f.read(), re.M)
-    if not m:
-        raise ValueError(f"{path}: no entry_point")
-    return int(m.group(1))
+    return int(toml_get(path, "object.entry_point"))
 
 
 def lvq8_compress(data: np.ndarray, mean: np.ndarray | None = None, device: int = 0):
@@ -180,8 +182,31 @@ class Vamana:
     def __init__(self, config_path, graph_loader, data_loader, distance: DistanceType = DistanceType.L2,
                  query_type: DataType = DataType.float32, enforce_dims: bool = False, num_threads: int = 1,
                  device: int = 0):
+        self._query_type = query_type
+        self._enforce_dims = bool(enforce_dims)
+        if isinstance(graph_loader, GraphLoader) and isinstance(data_loader, VectorDataLoader):
+            # files: streamed straight into HBM by the library (svsb200_index_assemble), no host copy
+            self._lib = _lib.lib()
+            self._distance = DistanceType(distance)
+            self._dtype = data_loader.data_type.value
+            self._params = VamanaSearchParameters()
+            self._num_threads = int(num_threads)
+            devices = [int(d) for d in device] if isinstance(device, (list, tuple)) else [int(device)]
+            handle = C.c_void_p()
+            _lib.check(self._lib.svsb200_index_assemble(
+                os.fsencode(str(config_path)), os.fsencode(graph_loader.path), os.fsencode(data_loader.path),
+                _DTYPE_CODE[self._dtype], int(data_loader.dims), int(self._distance), (C.c_int * len(devices))(*devices),
+                len(devices), C.byref(handle)))
+            self._h = handle
+            # index.apply(config): the saved search parameters become the defaults (index.h:1047-1048)
+            w, c = self.get_option("config_search_window_size"), self.get_option("config_search_buffer_capacity")
+            self._params.buffer_config = SearchBufferConfig(w, max(w, c))
+            self._params.search_buffer_visited_set = bool(self.get_option("config_search_buffer_visited_set"))
+            return
         graph = graph_loader.load() if hasattr(graph_loader, "load") else np.asarray(graph_loader)
         data = data_loader.load() if hasattr(data_loader, "load") else np.asarray(data_loader)
+        if getattr(data_loader, "dims", 0) and data.shape[1] != data_loader.dims:
+            raise ValueError(f"the data file holds {data.shape[1]}-dimensional vectors, {data_loader.dims} expected")
         self._init(data, graph, _read_entry_point(config_path), distance, device, num_threads)
 
     @classmethod
@@ -295,6 +320,10 @@ class Vamana:
             raise ValueError("queries must be a 2-D array")
         if q.dtype not in _DTYPE_CODE:
             raise TypeError(f"unsupported query type {q.dtype}")
+        qt = getattr(self, "_query_type", None)
+        if qt is not None and q.dtype != qt.value:
+            # the reference compiles one specialisation per declared query type (bindings/python/src/vamana.cpp:88-160)
+            raise TypeError(f"this index was assembled for {qt.name} queries, got {q.dtype}")
         if q.shape[1] != self.dimensions:
             raise ValueError(f"Query has dimension {q.shape[1]}, index has {self.dimensions}")
         nq, k = q.shape[0], int(n_neighbors)

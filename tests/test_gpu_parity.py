@@ -245,10 +245,29 @@ def test_assemble_from_files_like_the_reference_binding(dataset, ref_outputs, tm
     from scalablevectorsearch_b200 import DataType, DistanceType, GraphLoader, Vamana, VectorDataLoader, io
     io.write_svs(str(tmp_path / "data.svs"), dataset.data)
     io.write_svs(str(tmp_path / "graph.svs"), dataset.graph)
-    (tmp_path / "config.toml").write_text(f"[object]\nentry_point = {dataset.entry_point}\n")
+    (tmp_path / "config.toml").write_text(
+        f"[object]\nentry_point = {dataset.entry_point}\n[object.search_parameters]\nsearch_window_size = 7\n"
+        "search_buffer_capacity = 9\n")
     index = Vamana(str(tmp_path / "config.toml"), GraphLoader(str(tmp_path / "graph.svs")),
-                   VectorDataLoader(str(tmp_path / "data.svs"), DataType.float32), distance=DistanceType.Cosine)
+                   VectorDataLoader(str(tmp_path / "data.svs"), DataType.float32, dims=128), distance=DistanceType.Cosine)
     assert (index.size, index.dimensions, index.graph_max_degree) == (10000, 128, 128)
+    # index.apply(config): the saved search parameters are the defaults (index/vamana/index.h:1047-1048)
+    cfg = index.search_parameters.buffer_config
+    assert (cfg.search_window_size, cfg.search_buffer_capacity) == (7, 9)
+    from scalablevectorsearch_b200 import Svsb200Error
+    with pytest.raises(Svsb200Error):      # VectorDataLoader(dims=...) is checked against the file
+        Vamana(str(tmp_path / "config.toml"), GraphLoader(str(tmp_path / "graph.svs")),
+               VectorDataLoader(str(tmp_path / "data.svs"), DataType.float32, dims=96))
+    with pytest.raises(TypeError):         # declared query type (default float32) is enforced
+        index.search(dataset.queries[:4].astype(np.float16), 10)
+    # the same data as .fvecs goes through the strided vecs reader
+    io.write_vecs(str(tmp_path / "data.fvecs"), dataset.data)
+    index2 = Vamana(str(tmp_path / "config.toml"), GraphLoader(str(tmp_path / "graph.svs")),
+                    VectorDataLoader(str(tmp_path / "data.fvecs"), DataType.float32), distance=DistanceType.Cosine)
+    index2.search_window_size = 100
+    i2, d2 = index2.search(dataset.queries[100:], 10)
+    assert_same((i2, d2), ref_outputs["cosine_f32_f32_w100_c100_ids"], ref_outputs["cosine_f32_f32_w100_c100_dists"],
+                "assemble from fvecs")
     index.search_window_size = 100
     assert index.search_parameters.buffer_config.search_buffer_capacity == 100
     ids, dists = index.search(dataset.queries[100:], 10)

@@ -69,3 +69,39 @@ def test_synthetic_generator_is_deterministic_and_unit_norm():
     assert np.array_equal(a, b) and np.array_equal(qa, qb)
     assert np.allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-5)
     assert a.dtype == np.float32 and qa.shape == (50, 96)
+
+
+def test_toml_subset_reader(tmp_path):
+    """The library's own TOML reader (svsb200_toml_get) on the reference's saved-configuration shape
+    (data/test_dataset/vamana_config.toml): nested tables, indentation, comments, strings, booleans, floats."""
+    from scalablevectorsearch_b200 import Svsb200Error
+    from scalablevectorsearch_b200.vamana import toml_get
+    p = tmp_path / "svs_config.toml"
+    p.write_text("""# comment
+__version__ = 'v0.0.2'   # trailing comment
+
+[object]
+__schema__ = 'vamana_index_parameters'
+entry_point = 9426
+name = "vamana # not a comment"
+
+    [object.build_parameters]
+    alpha = 1.2000000476837158
+    use_full_search_history = true
+
+    [object.search_parameters]
+    search_buffer_capacity = 40
+    search_window_size = 24
+[[ignored.array]]
+x = 1
+""")
+    assert toml_get(str(p), "object.entry_point") == "9426"
+    assert toml_get(str(p), "__version__") == "v0.0.2"
+    assert toml_get(str(p), "object.name") == "vamana # not a comment"
+    assert float(toml_get(str(p), "object.build_parameters.alpha")) == pytest.approx(1.2)
+    assert toml_get(str(p), "object.build_parameters.use_full_search_history") == "true"
+    assert toml_get(str(p), "object.search_parameters.search_window_size") == "24"
+    with pytest.raises(Svsb200Error):
+        toml_get(str(p), "ignored.array.x")
+    with pytest.raises(Svsb200Error):
+        toml_get(str(p), "object.missing")
