@@ -169,6 +169,23 @@ int svsb200_set_option(svsb200_index* index, const char* name, long value);
  * "generic_kernel" (set to 1 to force the generic kernel; results are identical). */
 int svsb200_get_option(svsb200_index* index, const char* name, long* value);
 
+/* The filtered and range searches of the reference's runtime ABI (svs::runtime::v0::VamanaIndex::search with an
+ * IDFilter, ::range_search; bindings/cpp/include/svs/runtime/vamana_index.h:75-92, implemented in
+ * bindings/cpp/src/vamana_index_impl.h:139-300 with a batch iterator that keeps asking for further candidates).
+ * Here the membership test runs on the device: the caller hands the filter over as a bitmap of n bits
+ * (bit i = id i may be returned), every query searches with a result list that grows (x4) until k members were
+ * found or the search is exhausted, and the first k members in result order are returned -- distances are the graph
+ * search's.  Short rows are padded with id = all-ones, distance = +inf (the reference's `Unspecify`).
+ *   svsb200_range_search returns, per query, the results closer than `radius` (further than, for MIP):
+ *   counts[nq] and two malloc'ed arrays holding the concatenated ids / distances (release with svsb200_free). */
+int svsb200_search_filtered(
+    svsb200_index* index, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+    const uint32_t* id_bitmap, uint64_t* out_ids, float* out_dists, uint32_t* out_found);
+int svsb200_range_search(
+    svsb200_index* index, const void* queries, int qdtype, size_t nq, float radius, size_t window,
+    uint32_t* out_counts, uint64_t** out_ids, float** out_dists);
+void svsb200_free(void* p);
+
 /* Mode B of SURVEY.md §8e inside one process: `shards[s]` are single-device indexes over disjoint,
  * contiguous id ranges of one dataset, each with its own graph and entry point and its id range's first id
  * set with svsb200_set_id_offset.  Every query is searched on every shard; the per-shard top-k rows are

@@ -503,6 +503,57 @@ __global__ void lvq8_compress_kernel(const float* __restrict__ data, uint32_t n,
     }
 }
 
+// Filtered search (bindings/cpp/src/vamana_index_impl.h:139-218): out of a query's `kk` search results (sorted), keep
+// the first k whose id is a member of the filter bitmap; `found[q]` = how many there were.
+__global__ void filter_topk_kernel(const uint64_t* __restrict__ ids, const float* __restrict__ dists, uint32_t nq, uint32_t kk,
+                                   uint32_t k, const uint32_t* __restrict__ bitmap, uint64_t* __restrict__ out_ids,
+                                   float* __restrict__ out_dists, uint32_t* __restrict__ found, uint32_t* __restrict__ unfinished) {
+    const uint32_t q = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const uint32_t lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    uint32_t cnt = 0;
+    bool exhausted = false;   // the search returned fewer than kk valid entries: nothing more to find
+    for (uint32_t j0 = 0; j0 < kk && cnt < k; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        const uint64_t id = j < kk ? ids[size_t(q) * kk + j] : ~uint64_t(0);
+        const bool valid = id != ~uint64_t(0);
+        const bool pass = valid && ((bitmap[id >> 5] >> (id & 31)) & 1u);
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, pass);
+        const uint32_t o = cnt + __popc(m & ((1u << lane) - 1u));
+        if (pass && o < k) {
+            out_ids[size_t(q) * k + o] = id;
+            out_dists[size_t(q) * k + o] = dists[size_t(q) * kk + j];
+        }
+        cnt += __popc(m);
+        if (__any_sync(0xFFFFFFFFu, j < kk && !valid)) exhausted = true;
+    }
+    cnt = min(cnt, k);
+    if (lane == 0) {
+        found[q] = cnt;
+        if (cnt < k && !exhausted) atomicAdd(unfinished, 1u);
+    }
+}
+
+// Range search (vamana_index_impl.h:227-300): number of a query's sorted results inside the radius; a query whose
+// last result is still inside needs a longer list.
+__global__ void range_count_kernel(const float* __restrict__ dists, const uint64_t* __restrict__ ids, uint32_t nq, uint32_t kk,
+                                   float radius, int greater, uint32_t* __restrict__ counts, uint32_t* __restrict__ unfinished) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    uint32_t c = 0;
+    bool exhausted = false;
+    for (; c < kk; ++c) {
+        if (ids[size_t(q) * kk + c] == ~uint64_t(0)) {
+            exhausted = true;
+            break;
+        }
+        const float d = dists[size_t(q) * kk + c];
+        if (greater ? !(d > radius) : !(d < radius)) break;
+    }
+    counts[q] = c;
+    if (c == kk && !exhausted) atomicAdd(unfinished, 1u);
+}
+
 template <int QT>
 static cudaError_t launch_prepare(const void* d_queries, uint32_t nq, uint32_t dim, uint32_t qstride, int mode, int metric,
                                   int code_type, float scale, float bias, const float* mean, float* qf, uint8_t* qcodes,
@@ -1404,6 +1455,153 @@ int svsb200_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq
     return svsb200_search_cancellable(ix, queries, qdtype, nq, k, window, capacity, use_visited_set, out_ids, id_bytes,
                                       out_dists, stream_, nullptr, nullptr);
 }
+
+// Runs the batch with a result list of `kk` entries per query (window = capacity = max(window, kk)) into the scratch's
+// own id / distance blocks.
+static int search_long_lists(svsb200_index* ix, Replica* rep, Scratch* sc, const void* d_queries, int qdtype, size_t nq, size_t kk,
+                             size_t window) {
+    CUDA_TRY(sc->ids.ensure(nq * kk * 8));
+    CUDA_TRY(sc->dists.ensure(nq * kk));
+    const size_t w = std::max(window, kk);
+    return search_on_device(ix, rep, sc, d_queries, qdtype, nq, kk, w, w, sc->ids.ptr, 8, sc->dists.ptr, sc->stream);
+}
+
+int svsb200_search_filtered(svsb200_index* ix, const void* queries, int qdtype, size_t nq, size_t k, size_t window,
+                            const uint32_t* id_bitmap, uint64_t* out_ids, float* out_dists, uint32_t* out_found) {
+    if (!ix) return fail("svsb200_search_filtered: NULL index");
+    if (nq == 0) return 0;
+    if (!queries || !id_bitmap || !out_ids || !out_dists) return fail("svsb200_search_filtered: NULL buffer");
+    if (k == 0) return fail("k must be greater than 0");
+    if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    Scratch* sc = acquire(rep, &err);
+    if (!sc) return fail(err);
+    uint32_t *d_bitmap = nullptr, *d_found = nullptr;
+    uint64_t* d_oi = nullptr;
+    float* d_od = nullptr;
+    auto body = [&]() -> int {
+        const size_t words = (ix->n + 31) / 32;
+        const size_t qbytes = nq * ix->dim * esize(qdtype);
+        CUDA_TRY(cudaMalloc(&d_bitmap, words * 4));
+        CUDA_TRY(cudaMalloc(&d_found, (nq + 1) * 4));
+        CUDA_TRY(cudaMalloc(&d_oi, nq * k * 8));
+        CUDA_TRY(cudaMalloc(&d_od, nq * k * 4));
+        CUDA_TRY(sc->q_raw.ensure(qbytes));
+        CUDA_TRY(cudaMemcpyAsync(d_bitmap, id_bitmap, words * 4, cudaMemcpyHostToDevice, sc->stream));
+        CUDA_TRY(cudaMemcpyAsync(sc->q_raw.ptr, queries, qbytes, cudaMemcpyHostToDevice, sc->stream));
+        CUDA_TRY(cudaMemsetAsync(d_oi, 0xFF, nq * k * 8, sc->stream));
+        // lists grow (x4) until every query has k members or its search is exhausted, like the reference's batch
+        // iterator asks for further batches (vamana_index_impl.h:183-205)
+        size_t kk = std::max(k, window);
+        for (;;) {
+            kk = std::min(kk, ix->n);
+            int rc = search_long_lists(ix, rep, sc, sc->q_raw.ptr, qdtype, nq, kk, window);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(d_found + nq, 0, 4, sc->stream));
+            filter_topk_kernel<<<unsigned((nq + 3) / 4), 128, 0, sc->stream>>>(
+                reinterpret_cast<const uint64_t*>(sc->ids.ptr), sc->dists.ptr, uint32_t(nq), uint32_t(kk), uint32_t(k), d_bitmap,
+                d_oi, d_od, d_found, d_found + nq);
+            count_launch();
+            CUDA_TRY(cudaGetLastError());
+            uint32_t unfinished = 0;
+            CUDA_TRY(cudaMemcpyAsync(&unfinished, d_found + nq, 4, cudaMemcpyDeviceToHost, sc->stream));
+            CUDA_TRY(cudaStreamSynchronize(sc->stream));
+            if (unfinished == 0 || kk >= ix->n || kk >= 16384) break;
+            kk *= 4;
+        }
+        std::vector<uint32_t> found(nq);
+        CUDA_TRY(cudaMemcpyAsync(found.data(), d_found, nq * 4, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_ids, d_oi, nq * k * 8, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaMemcpyAsync(out_dists, d_od, nq * k * 4, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaStreamSynchronize(sc->stream));
+        for (size_t q = 0; q < nq; ++q) {   // pad like the reference: unspecified id (all-ones), +inf distance
+            for (size_t j = found[q]; j < k; ++j) {
+                out_ids[q * k + j] = ~uint64_t(0);
+                out_dists[q * k + j] = INFINITY;
+            }
+            if (out_found) out_found[q] = found[q];
+        }
+        return 0;
+    };
+    int rc = body();
+    if (d_bitmap) cudaFree(d_bitmap);
+    if (d_found) cudaFree(d_found);
+    if (d_oi) cudaFree(d_oi);
+    if (d_od) cudaFree(d_od);
+    release(rep, sc);
+    return rc;
+}
+
+int svsb200_range_search(svsb200_index* ix, const void* queries, int qdtype, size_t nq, float radius, size_t window,
+                         uint32_t* out_counts, uint64_t** out_ids, float** out_dists) {
+    if (!ix) return fail("svsb200_range_search: NULL index");
+    if (nq == 0) return 0;
+    if (!queries || !out_counts || !out_ids || !out_dists) return fail("svsb200_range_search: NULL buffer");
+    if (qdtype < SVSB200_F32 || qdtype > SVSB200_U8) return fail("bad query dtype");
+    *out_ids = nullptr;
+    *out_dists = nullptr;
+    Replica* rep = ix->reps[0].get();
+    CUDA_TRY(cudaSetDevice(rep->device));
+    std::string err;
+    Scratch* sc = acquire(rep, &err);
+    if (!sc) return fail(err);
+    uint32_t* d_counts = nullptr;
+    auto body = [&]() -> int {
+        const size_t qbytes = nq * ix->dim * esize(qdtype);
+        CUDA_TRY(cudaMalloc(&d_counts, (nq + 1) * 4));
+        CUDA_TRY(sc->q_raw.ensure(qbytes));
+        CUDA_TRY(cudaMemcpyAsync(sc->q_raw.ptr, queries, qbytes, cudaMemcpyHostToDevice, sc->stream));
+        size_t kk = std::max<size_t>(window, 16);
+        for (;;) {
+            kk = std::min(kk, ix->n);
+            int rc = search_long_lists(ix, rep, sc, sc->q_raw.ptr, qdtype, nq, kk, window);
+            if (rc) return rc;
+            CUDA_TRY(cudaMemsetAsync(d_counts + nq, 0, 4, sc->stream));
+            range_count_kernel<<<unsigned((nq + 127) / 128), 128, 0, sc->stream>>>(
+                sc->dists.ptr, reinterpret_cast<const uint64_t*>(sc->ids.ptr), uint32_t(nq), uint32_t(kk), radius,
+                ix->metric != SVSB200_L2, d_counts, d_counts + nq);
+            count_launch();
+            CUDA_TRY(cudaGetLastError());
+            uint32_t unfinished = 0;
+            CUDA_TRY(cudaMemcpyAsync(&unfinished, d_counts + nq, 4, cudaMemcpyDeviceToHost, sc->stream));
+            CUDA_TRY(cudaStreamSynchronize(sc->stream));
+            if (unfinished == 0 || kk >= ix->n || kk >= 16384) break;
+            kk *= 4;
+        }
+        CUDA_TRY(cudaMemcpyAsync(out_counts, d_counts, nq * 4, cudaMemcpyDeviceToHost, sc->stream));
+        std::vector<uint64_t> ids(nq * kk);
+        std::vector<float> dd(nq * kk);
+        CUDA_TRY(cudaMemcpyAsync(ids.data(), sc->ids.ptr, nq * kk * 8, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaMemcpyAsync(dd.data(), sc->dists.ptr, nq * kk * 4, cudaMemcpyDeviceToHost, sc->stream));
+        CUDA_TRY(cudaStreamSynchronize(sc->stream));
+        size_t total = 0;
+        for (size_t q = 0; q < nq; ++q) total += out_counts[q];
+        uint64_t* oi = static_cast<uint64_t*>(malloc(std::max<size_t>(total, 1) * 8));
+        float* od = static_cast<float*>(malloc(std::max<size_t>(total, 1) * 4));
+        if (!oi || !od) {
+            free(oi);
+            free(od);
+            return fail("svsb200_range_search: out of host memory");
+        }
+        size_t o = 0;
+        for (size_t q = 0; q < nq; ++q)
+            for (size_t j = 0; j < out_counts[q]; ++j, ++o) {
+                oi[o] = ids[q * kk + j];
+                od[o] = dd[q * kk + j];
+            }
+        *out_ids = oi;
+        *out_dists = od;
+        return 0;
+    };
+    int rc = body();
+    if (d_counts) cudaFree(d_counts);
+    release(rep, sc);
+    return rc;
+}
+
+void svsb200_free(void* p) { free(p); }
 
 int svsb200_search_sharded(svsb200_index* const* shards, size_t nshards, const void* queries, int qdtype, size_t nq,
                            size_t k, size_t window, size_t capacity, uint64_t* out_ids, float* out_dists) {

@@ -359,6 +359,43 @@ class Vamana:
         _lib.check(self._lib.svsb200_exhaustive_device(self._h, d_queries, _DTYPE_CODE[np.dtype(qdtype)], nq,
                                                        int(n_neighbors), d_ids, d_dists, stream or None))
 
+    def search_filtered(self, queries: np.ndarray, n_neighbors: int, allowed: np.ndarray):
+        """``svs::runtime::VamanaIndex::search(..., IDFilter*)`` (bindings/cpp/include/svs/runtime/vamana_index.h:75-83):
+        ``allowed`` is a boolean mask over the ids (the filter's ``is_member``), evaluated on the device.
+        Returns (ids uint64, distances, found per query); short rows are padded with all-ones / +inf."""
+        q = np.ascontiguousarray(queries)
+        mask = np.ascontiguousarray(allowed, dtype=bool)
+        if mask.shape != (self.size,):
+            raise ValueError("allowed must hold one boolean per indexed vector")
+        bitmap = np.packbits(mask, bitorder="little")
+        bitmap = np.concatenate([bitmap, np.zeros((-len(bitmap)) % 4, dtype=np.uint8)]).view(np.uint32)
+        nq, k = q.shape[0], int(n_neighbors)
+        ids = np.empty((nq, k), dtype=np.uint64)
+        dists = np.empty((nq, k), dtype=np.float32)
+        found = np.empty(nq, dtype=np.uint32)
+        _lib.check(self._lib.svsb200_search_filtered(self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, k,
+                                                     self._params.buffer_config.search_window_size, bitmap.ctypes.data,
+                                                     ids.ctypes.data, dists.ctypes.data, found.ctypes.data))
+        return ids, dists, found
+
+    def range_search(self, queries: np.ndarray, radius: float):
+        """``svs::runtime::VamanaIndex::range_search`` (vamana_index.h:85-92): per query, every graph-search result
+        closer than ``radius`` (greater than, for MIP).  Returns a list of (ids, distances) pairs."""
+        q = np.ascontiguousarray(queries)
+        nq = q.shape[0]
+        counts = np.empty(nq, dtype=np.uint32)
+        pi, pd = C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.svsb200_range_search(self._h, q.ctypes.data, _DTYPE_CODE[q.dtype], nq, float(radius),
+                                                  self._params.buffer_config.search_window_size, counts.ctypes.data,
+                                                  C.byref(pi), C.byref(pd)))
+        total = int(counts.sum())
+        ids = np.ctypeslib.as_array(C.cast(pi, C.POINTER(C.c_uint64)), shape=(max(total, 1),))[:total].copy()
+        dd = np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_float)), shape=(max(total, 1),))[:total].copy()
+        self._lib.svsb200_free(pi)
+        self._lib.svsb200_free(pd)
+        offs = np.concatenate([[0], np.cumsum(counts)])
+        return [(ids[offs[i]:offs[i + 1]], dd[offs[i]:offs[i + 1]]) for i in range(nq)]
+
     def flat_search(self, queries: np.ndarray, n_neighbors: int):
         """Exact top-k of every query over ALL base vectors -- what ``svs.Flat(...).search`` computes
         (index/flat/flat.h:421-465) -- on the tensor cores, with the graph search's bit-exact distances

@@ -471,3 +471,35 @@ def test_sharded_index_in_one_process_matches_reference_per_shard_plus_merge(dat
     ids, dists = sv.search(q, 10)
     want_i, want_d = merge_topk_reference_order(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]), 10, False)
     assert np.array_equal(ids.astype(np.int64), want_i) and np.array_equal(bits(dists), bits(want_d))
+
+
+def test_filtered_and_range_search(dataset, oracle):
+    """The runtime ABI's filtered / range searches (vamana_index.h:75-92) with the filter evaluated on the device:
+    checked against the oracle's plain search results post-processed on the host (members in result order; results
+    inside the radius)."""
+    from scalablevectorsearch_b200 import SearchBufferConfig
+    index = make_index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    index.search_parameters.buffer_config = SearchBufferConfig(64)
+    want = oracle.index(dataset.data, dataset.graph, dataset.entry_point, "l2")
+    q = dataset.queries[:100]
+    rng = np.random.default_rng(0)
+    allowed = rng.random(dataset.data.shape[0]) < 0.3
+    ids, dists, found = index.search_filtered(q, 10, allowed)
+    assert np.all(found == 10)
+    assert np.all(allowed[ids.astype(np.int64)])
+    assert np.all(np.diff(dists, axis=1) >= 0)
+    # a long oracle list holds the same members in the same order (first 10 allowed entries)
+    wi, wd = want.search(q, 256, 256, 256)
+    for i in range(len(q)):
+        keep = [j for j in range(256) if allowed[int(wi[i, j])]][:10]
+        if len(keep) == 10 and keep[-1] < 60:     # fully inside the first (window 64) list: identical by construction
+            assert np.array_equal(ids[i], wi[i, keep]) and np.array_equal(bits(dists[i]), bits(wd[i, keep]))
+    # nothing allowed -> empty rows, padded
+    ids0, d0, f0 = index.search_filtered(q[:5], 3, np.zeros(dataset.data.shape[0], dtype=bool))
+    assert np.all(f0 == 0) and np.all(ids0 == np.uint64(0xFFFFFFFFFFFFFFFF)) and np.all(np.isposinf(d0))
+    # range search: everything closer than the 20th-nearest distance of query 0
+    radius = float(wd[0, 20])
+    res = index.range_search(q[:8], radius)
+    for i, (ri, rd) in enumerate(res):
+        assert np.all(rd < radius) and np.all(np.diff(rd) >= 0)
+        assert len(ri) >= int(np.sum(wd[i, :50] < radius)) - 1
