@@ -503,3 +503,40 @@ def test_filtered_and_range_search(dataset, oracle):
     for i, (ri, rd) in enumerate(res):
         assert np.all(rd < radius) and np.all(np.diff(rd) >= 0)
         assert len(ri) >= int(np.sum(wd[i, :50] < radius)) - 1
+
+
+def test_runtime_abi_demo_program(tmp_path):
+    """A C++ program written against the reference's runtime header only (svs::runtime::v0::VamanaIndex: build / add /
+    search / IDFilter / range_search / get_distance), linked with libsvsb200_runtime.so instead of libsvs_runtime."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe = os.path.join(ROOT, "scalablevectorsearch_b200", "cpp", "_build", "runtime_demo")
+    if not os.path.exists(exe):
+        pytest.skip("runtime_demo not built (needs the reference's runtime headers at build time)")
+    rng = np.random.default_rng(4)
+    n, dim, nq, k = 5000, 32, 16, 5
+    x = rng.standard_normal((n, dim)).astype(np.float32)
+    q = rng.standard_normal((nq, dim)).astype(np.float32)
+    x.tofile(tmp_path / "x.f32")
+    q.tofile(tmp_path / "q.f32")
+    out = subprocess.run([exe, str(tmp_path / "x.f32"), str(n), str(dim), str(tmp_path / "q.f32"), str(nq)],
+                         capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    rows = {"plain": [], "even": [], "range": [], "get_distance": []}
+    for line in out.stdout.splitlines():
+        tag, label, dist = line.split()
+        rows[tag].append((int(label), float(dist)))
+    d = ((q[:, None, :] - x[None, :, :]) ** 2).sum(-1)
+    gt = np.argsort(d, axis=1)[:, :k]
+    plain = np.array([r[0] for r in rows["plain"]]).reshape(nq, k)
+    recall = np.mean([len(set(plain[i]) & set(gt[i])) for i in range(nq)]) / k
+    assert recall > 0.9, recall
+    even = np.array([r[0] for r in rows["even"]]).reshape(nq, k)
+    assert np.all(even % 2 == 0)
+    gt_even = np.argsort(np.where(np.arange(n)[None, :] % 2 == 0, d, np.inf), axis=1)[:, :k]
+    assert np.mean([len(set(even[i]) & set(gt_even[i])) for i in range(nq)]) / k > 0.85
+    radius = rows["plain"][k - 1][1]
+    assert rows["range"] and all(dist < radius for _, dist in rows["range"])
+    label, dist = rows["get_distance"][0]
+    assert label == rows["plain"][0][0] and dist == pytest.approx(rows["plain"][0][1], rel=1e-6)
