@@ -435,11 +435,18 @@ def run_ours(args):
             ncu_traffic = json.load(open(ncu_path)).get(args.workload, {}).get("dram_bytes_per_launch")
         # recall@10 on a sample against the exact top-k (svsb200_exhaustive_device: the search path's own distance code,
         # ties by id; checked against the oracle in tests/test_gpu_parity.py::test_exhaustive_scan_is_exact_topk)
-        sample = min(1000, nq)
+        # (uncompressed data: the tensor-core flat search over the whole batch -- exact by construction, equal to that
+        # scan bit for bit, tests/test_gpu_flat.py; LVQ-8: the scan on a 1000-query sample)
+        sample = nq if lvq is None else min(1000, nq)
         gt_ids = torch.empty((sample, k), dtype=torch.int64, device=dev)
         gt_d = torch.empty((sample, k), dtype=torch.float32, device=dev)
-        index.exhaustive_device(q_dev.data_ptr(), queries.dtype, sample, k, gt_ids.data_ptr(), gt_d.data_ptr(),
-                                stream=torch.cuda.current_stream(dev).cuda_stream or 1)
+        gt_stream = torch.cuda.current_stream(dev).cuda_stream or 1
+        if lvq is None:
+            index.flat_search_device(q_dev.data_ptr(), queries.dtype, sample, k, gt_ids.data_ptr(), gt_d.data_ptr(),
+                                     stream=gt_stream)
+        else:
+            index.exhaustive_device(q_dev.data_ptr(), queries.dtype, sample, k, gt_ids.data_ptr(), gt_d.data_ptr(),
+                                    stream=gt_stream)
         torch.cuda.synchronize()
         gt = gt_ids.cpu().numpy()
         got = ids_all[:sample].cpu().numpy()

@@ -69,6 +69,7 @@ struct SearchParams {
     uint32_t* evals;
     uint32_t* fetched;           // rows actually read from HBM (after the visited filter)
     const int* cancel;           // optional device flag: non-zero stops the batch (polled per query and per hop)
+    uint32_t exh_split;          // exhaustive scan: base rows are cut into this many ranges, one work item per (query, range)
     // graph builder only (HIST kernels): per query, every expanded node {key bits, id}
     uint2* hist;
     uint32_t* hist_count;

@@ -21,10 +21,12 @@
 //      Queries that fail the test (rare) are searched again with the exact scan kernel -- the result is exact
 //      in every case.
 //
-// Error bound: with q~, x~ the fp16-rounded operands (relative rounding 2^-11 per element),
-//   |q~.x~ - q.x| <= ||q~ - q|| ||x~|| + ||q|| ||x~ - x|| <= 2^-10 ||q|| ||x|| (1 + 2^-12),
-// the tensor-core accumulation adds at most dim * 2^-22 ||q|| ||x||, and for L2 the bias |x~|^2 differs from |x|^2
-// by at most 2^-10 ||x||^2; so |key~ - key| <= E(q) := 2^-9 (||q|| + Xmax)^2 + dim 2^-20 ||q|| Xmax for both metrics.
+// Error bound: with q~, x~ the fp16-rounded operands (relative rounding 2^-11 per element; float16 inputs are
+// not rounded at all), r = the number of rounded operands (0..2):
+//   |q~.x~ - q.x| <= ||q~ - q|| ||x~|| + ||q|| ||x~ - x|| <= r 2^-11 ||q|| ||x|| (1 + 2^-11),
+// the products are exact in fp32 and the tensor-core accumulation of `dim` of them adds at most dim 2^-22 ||q|| ||x||;
+// for L2 the bias |x~|^2 differs from |x|^2 by at most 2^-10 ||x||^2 when the data was rounded.  So
+//   E_ip(q) = (r 2^-11 + dim 2^-22) ||q|| Xmax,      E_l2(q) = 2 E_ip(q) + [data rounded] 2^-10 Xmax^2.
 #include "search_kernel.cuh"
 
 #include <cuda_fp16.h>
@@ -251,11 +253,24 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                // keys of the 32 columns; only when the smallest beats the threshold (rare once the list has
+                // settled) are they looked at one by one
+                float key[32];
+                float best = INFINITY;
 #pragma unroll
-                for (uint32_t i = 0; i < 32; ++i) {
-                    const float key = fmaf(fp.key_scale, __uint_as_float(v[i]), bias[c * 32 + i]);
-                    if (key < __uint_as_float(uint32_t(st)))   // rare: the list changes (out of line)
-                        st = flat_list_insert(lkey, lid, row, st, key, nt * FLAT_BN + c * 32 + i);
+                for (uint32_t i4 = 0; i4 < 8; ++i4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + c * 32 + i4 * 4);
+                    key[4 * i4 + 0] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 0]), b4.x);
+                    key[4 * i4 + 1] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 1]), b4.y);
+                    key[4 * i4 + 2] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 2]), b4.z);
+                    key[4 * i4 + 3] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 3]), b4.w);
+                    best = fminf(fminf(fminf(best, key[4 * i4 + 0]), fminf(key[4 * i4 + 1], key[4 * i4 + 2])), key[4 * i4 + 3]);
+                }
+                if (best < __uint_as_float(uint32_t(st))) {
+#pragma unroll
+                    for (uint32_t i = 0; i < 32; ++i)
+                        if (key[i] < __uint_as_float(uint32_t(st)))
+                            st = flat_list_insert(lkey, lid, row, st, key[i], nt * FLAT_BN + c * 32 + i);
                 }
             }
             tc_fence_before();
@@ -333,6 +348,7 @@ struct RescoreParams {
     uint32_t* unverified;     // list of query indices that need the exact scan
     uint32_t* n_unverified;
     float ksign;
+    int data_rounded;         // the base vectors were float32 (rounded to fp16 for the GEMM)
 };
 
 template <int ROWT, int OP>
@@ -402,7 +418,9 @@ __global__ void __launch_bounds__(32, 16) flat_rescore_kernel(const __grid_const
     for (int o = 16; o; o >>= 1) kth_approx = fminf(kth_approx, __shfl_xor_sync(FULL, kth_approx, o));
     // |approximate key - key| <= E(q) (header): excluded rows are provably outside the exact top k iff T > kth + 2E
     const float qn = rp.qnorm[q], xm = __uint_as_float(*rp.xmax_bits);
-    const float E = 0.001953125f * (qn + xm) * (qn + xm) + float(p.dim) * 9.5367431640625e-7f * qn * xm;
+    const float rounded = p.scale;   // operands that were rounded to fp16 (0, 1 or 2)
+    const float e_ip = (rounded * 4.8828125e-4f + float(p.dim) * 2.384185791015625e-7f) * qn * xm * 1.0001f;   // 2^-11 each, dim 2^-22
+    const float E = p.greater ? e_ip : 2.0f * e_ip + (rounded > 1.5f || rp.data_rounded ? 9.765625e-4f * xm * xm : 0.0f);
     const bool verified = C >= rp.k && T > kth_approx + 2.0f * E;
     if (lane == 0 && !verified) rp.unverified[atomicAdd(rp.n_unverified, 1u)] = q;
 }
@@ -484,6 +502,7 @@ cudaError_t flat_rescore(int rowt, int op, const SearchParams& p, const float* c
     rp.unverified = unverified;
     rp.n_unverified = n_unverified;
     rp.ksign = p.greater ? -1.0f : 1.0f;
+    rp.data_rounded = rowt == SVSB200_F32;
     return rowt == SVSB200_F32 ? rescore_rowt<SVSB200_F32>(op, p, rp, stream) : rescore_rowt<SVSB200_F16>(op, p, rp, stream);
 }
 

@@ -607,7 +607,20 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
         uint32_t q = 0;
         if (lane == 0) q = atomicAdd(p.work_counter, 1u);
         q = __shfl_sync(FULL, q, 0);
-        if (q >= p.nq) break;
+        // EXH: a work item is (query, range of base rows); its top-k goes to row [range][query] of the output
+        uint32_t exh_lo = 0, exh_hi = p.n, out_row = q;
+        if constexpr (EXH) {
+            const uint32_t splits = p.exh_split ? p.exh_split : 1u;
+            if (q >= p.nq * splits) break;
+            const uint32_t rg = q / p.nq;
+            out_row = q;                      // == rg * nq + query
+            q -= rg * p.nq;
+            const uint32_t chunk = (p.n + splits - 1) / splits;
+            exh_lo = min(p.n, rg * chunk);
+            exh_hi = min(p.n, exh_lo + chunk);
+        } else {
+            if (q >= p.nq) break;
+        }
         // cancellation between queries (extensions.h:579)
         if (p.cancel && *reinterpret_cast<const volatile int*>(p.cancel)) break;
 
@@ -640,7 +653,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
             }
             __syncwarp();
         }
-        uint32_t scan_base = 0;   // EXH: first id of the current block
+        uint32_t scan_base = exh_lo;   // EXH: first id of the current block
         uint32_t staged_node = kNoNeighbor;   // node whose adjacency row sits in adj[staged_buf]
         uint32_t staged_buf = 0;
 
@@ -650,8 +663,8 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
             if (p.cancel && *reinterpret_cast<const volatile int*>(p.cancel)) break;
             uint32_t deg = 0;
             if constexpr (EXH) {
-                if (scan_base >= p.n) break;
-                deg = min(p.deg_pad, p.n - scan_base);
+                if (scan_base >= exh_hi) break;
+                deg = min(p.deg_pad, exh_hi - scan_base);
                 for (uint32_t i = lane; i < deg; i += 32) cid[i] = scan_base + i;
                 scan_base += deg;
                 __syncwarp();
@@ -838,7 +851,7 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
             const bool valid = j < size;
             const uint32_t id = valid ? (bid[j] & kIdMask) : 0xFFFFFFFFu;
             const float dist = valid ? __fmul_rn(bkey[j], ksign) : (p.greater ? -INFINITY : INFINITY);
-            const size_t o = size_t(q) * p.k + j;
+            const size_t o = size_t(out_row) * p.k + j;
             if (p.id_bytes == 8)
                 reinterpret_cast<uint64_t*>(p.out_ids)[o] = valid ? uint64_t(id) + p.id_offset : ~uint64_t(0);
             else
@@ -883,7 +896,7 @@ template <int ROWT, int OP> cudaError_t launch_exhaustive(const SearchParams& p,
     err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kernel, cfg.warps_per_cta * 32, cfg.smem_bytes);
     if (err != cudaSuccess) return err;
     int grid = -cfg.grid * (resident > 0 ? resident : 1);
-    const int needed = int((p.nq + cfg.warps_per_cta - 1) / cfg.warps_per_cta);
+    const int needed = int((size_t(p.nq) * (p.exh_split ? p.exh_split : 1u) + cfg.warps_per_cta - 1) / cfg.warps_per_cta);
     if (grid > needed) grid = needed;
     kernel<<<grid, cfg.warps_per_cta * 32, cfg.smem_bytes, cfg.stream>>>(p);
     count_launch();

@@ -78,6 +78,8 @@ struct Scratch {
     DeviceBuffer<unsigned char> q_raw, q_codes, ids;
     DeviceBuffer<float> q_f32, q_aux, dists;
     DeviceBuffer<uint32_t> hops, evals, fetched;
+    DeviceBuffer<uint64_t> exh_ids;                    // exhaustive scan split over base ranges: per-range top-k
+    DeviceBuffer<float> exh_dists;
     DeviceBuffer<unsigned char> flat_a, flat_q2;       // tensor-core flat search: query tiles, gathered queries
     DeviceBuffer<float> flat_qnorm, flat_ckey, flat_d2;
     DeviceBuffer<uint32_t> flat_cid, flat_unv;         // candidates, unverified list (+ its counter in slot 0)
@@ -95,6 +97,7 @@ struct Scratch {
         q_raw.release(); q_codes.release(); ids.release(); q_f32.release(); q_aux.release(); dists.release();
         hops.release(); evals.release(); fetched.release();
         gather_ids.release(); merged_ids.release(); gather_dists.release(); merged_dists.release();
+        exh_ids.release(); exh_dists.release();
         flat_a.release(); flat_q2.release(); flat_qnorm.release(); flat_ckey.release(); flat_d2.release();
         flat_cid.release(); flat_unv.release(); flat_i2.release();
         if (d_counter) cudaFree(d_counter);
@@ -1286,12 +1289,32 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     CUDA_TRY(cudaEventRecord(sc->ev_start, stream));
     const int rowt = ix->storage == SVSB200_LVQ8 ? ROW_LVQ8 : ix->dtype;
     if (exhaustive) {
+        // few queries: cut the base rows into ranges so that (query, range) work items fill the GPU; the per-range
+        // top-k lists are merged with TotalOrder (== the scan's own order: key, then id)
+        const size_t want_items = size_t(rep->sm_count) * 32;
+        uint32_t split = uint32_t(std::min<size_t>(64, std::max<size_t>(1, want_items / nq)));
+        while (split > 1 && ix->n / split < 4 * k + 64) --split;
+        if (split > 1) {
+            CUDA_TRY(sc->exh_ids.ensure(size_t(split) * nq * k));
+            CUDA_TRY(sc->exh_dists.ensure(size_t(split) * nq * k));
+            p.out_ids = sc->exh_ids.ptr;
+            p.out_dists = sc->exh_dists.ptr;
+            p.exh_split = split;
+        }
         switch (rowt) {
             case ROW_LVQ8: err = launch_search_exhaustive<ROW_LVQ8>(op, p, cfg); break;
             case SVSB200_F32: err = launch_search_exhaustive<SVSB200_F32>(op, p, cfg); break;
             case SVSB200_F16: err = launch_search_exhaustive<SVSB200_F16>(op, p, cfg); break;
             case SVSB200_I8: err = launch_search_exhaustive<SVSB200_I8>(op, p, cfg); break;
             default: err = launch_search_exhaustive<SVSB200_U8>(op, p, cfg);
+        }
+        if (err == cudaSuccess && split > 1) {
+            const unsigned warps = 4;
+            merge_topk_kernel<<<unsigned((nq + warps - 1) / warps), warps * 32, 0, stream>>>(
+                sc->exh_ids.ptr, sc->exh_dists.ptr, split, uint32_t(nq), uint32_t(k), metric != SVSB200_L2,
+                static_cast<uint64_t*>(d_out_ids), d_out_dists);
+            count_launch();
+            err = cudaGetLastError();
         }
     } else if (use_fast) {
         switch (rowt) {
@@ -1846,6 +1869,8 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
     p.nq = uint32_t(nq);
     p.k = uint32_t(k);
     CUDA_TRY(cudaMemsetAsync(sc->flat_unv.ptr, 0, 4, stream));
+    // rounding terms of E(q) (flat.cu header): the query is always rounded to fp16, float32 data too
+    p.scale = (qdtype == SVSB200_F32 ? 1.0f : 0.0f) + (ix->dtype == SVSB200_F32 ? 1.0f : 0.0f);   // number of rounded operands
     CUDA_TRY(flat_rescore(ix->dtype, l2 ? OP_L2F : OP_IPF, p, sc->flat_ckey.ptr, sc->flat_cid.ptr, nsplit, uint32_t(nq), uint32_t(k),
                           sc->flat_qnorm.ptr, rep->flat_xmax, d_out_ids, d_out_dists, sc->flat_unv.ptr + 1, sc->flat_unv.ptr, stream));
     // queries whose bound did not verify: exact scan, results scattered over the rescored rows
