@@ -87,6 +87,18 @@ def build_graph_cached(tag, w, base, rank_builds, barrier):
     key = hashlib.sha1(json.dumps({k: w.get(k) for k in ("n", "dim", "dtype", "metric", "max_degree", "build_window",
                                                            "alpha", "builder")}, sort_keys=True).encode()).hexdigest()[:12]
     cache = os.path.join(os.environ.get("SVSB200_CACHE", "/tmp/svsb200_cache"), f"graph_{tag}_{key}.npy")
+    if w.get("per_shard_data") and w.get("builder") == "gpu":
+        # multi-GB shard graphs: built in place on this rank's GPU, never written to disk
+        from scalablevectorsearch_b200 import DistanceType, VamanaBuildParameters, build_graph
+        t1 = time.time()
+        graph, ep = build_graph(base, {"l2": DistanceType.L2, "ip": DistanceType.MIP}[w["metric"]],
+                                VamanaBuildParameters(alpha=w["alpha"], graph_max_degree=w["max_degree"],
+                                                      window_size=w["build_window"]),
+                                device=int(os.environ.get("LOCAL_RANK", 0)))
+        log(f"GPU graph build {tag} n={base.shape[0]} dim={base.shape[1]} R={w['max_degree']}: {time.time() - t1:.1f} s, "
+            f"avg degree {graph[:, 0].mean():.1f}")
+        barrier()
+        return ep, graph
     if rank_builds and not os.path.exists(cache) and w.get("builder") == "gpu":
         from scalablevectorsearch_b200 import DistanceType, VamanaBuildParameters, build_graph
         os.makedirs(os.path.dirname(cache), exist_ok=True)
