@@ -222,7 +222,7 @@ int svsb200_lvq8_compress(const float* data, size_t n, size_t dim, const float* 
  * (include/svs/index/vamana/index.h:404-440,968-994) and VamanaBuilder::construct
  * (index/vamana/vamana_build.h:221-599): medoid entry point (core/medioid.h:292-330), two passes over
  * batches of max(40, n/4096) rounds, greedy search with full search history + alpha-robust pruning
- * (prune.h: Progressive strategy for L2, Iterative for MIP), reverse edges with overflow re-pruning to
+ * (prune.h: Progressive strategy for L2, Iterative for MIP and cosine), reverse edges with overflow re-pruning to
  * `prune_to`.  Arguments are VamanaBuildParameters (index/vamana/build_params.h): 0 selects the reference's
  * default (alpha 1.2 / 0.95, max_candidate_pool_size = 3 * window_size, prune_to = max_degree - 4).
  *   vectors     n x dim float32 / float16 rows in HOST memory (row_stride_bytes apart, 0 = dense);

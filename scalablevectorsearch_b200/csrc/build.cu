@@ -125,11 +125,12 @@ __global__ void export_graph_kernel(const uint32_t* __restrict__ graph, const ui
 // batch rows [first, first+count) as prepared fp32 queries (exact conversion, zero padding)
 template <int ROWT>
 __global__ void batch_queries_kernel(const char* __restrict__ vectors, uint32_t row_stride, uint32_t dim, uint32_t qstride,
-                                     uint32_t first, uint32_t count, float* __restrict__ qf) {
+                                     uint32_t first, uint32_t count, float* __restrict__ qf, float* __restrict__ qaux) {
     const uint32_t q = blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const uint32_t lane = threadIdx.x & 31;
     if (q >= count) return;
     const char* row = vectors + size_t(first + q) * row_stride;
+    float sq = 0.f;
     for (uint32_t i = lane; i < qstride; i += 32) {
         float v = 0.f;
         if (i < dim) {
@@ -137,6 +138,12 @@ __global__ void batch_queries_kernel(const char* __restrict__ vectors, uint32_t 
             else v = __half2float(reinterpret_cast<const __half*>(row)[i]);
         }
         qf[size_t(q) * qstride + i] = v;
+        sq = fmaf(v, v, sq);
+    }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+    if (lane == 0) {   // {a_norm, unused}: the cosine query norm (cosine.h:117-119)
+        qaux[2 * size_t(q)] = sqrtf(sq);
+        qaux[2 * size_t(q) + 1] = 0.f;
     }
 }
 
@@ -155,7 +162,7 @@ extern "C" int svsb200_build_vamana(const void* vectors, int dtype, size_t n, si
                                     uint32_t* entry_point_out) {
     if (!vectors || !graph_rows_out || !entry_point_out) return set_error("svsb200_build_vamana: NULL argument");
     if (dtype != SVSB200_F32 && dtype != SVSB200_F16) return set_error("svsb200_build_vamana: float32 / float16 data only");
-    if (metric != SVSB200_L2 && metric != SVSB200_IP) return set_error("svsb200_build_vamana: L2 and MIP are supported");
+    if (metric < SVSB200_L2 || metric > SVSB200_COSINE) return set_error("svsb200_build_vamana: bad metric");
     if (n < 2 || dim == 0 || n >= (size_t(1) << 31)) return set_error("svsb200_build_vamana: bad shape");
     if (graph_max_degree == 0 || graph_max_degree > 32u * kFastMaxGW) return set_error("svsb200_build_vamana: graph_max_degree must be in [1, 128]");
     if (window_size == 0) return set_error("svsb200_build_vamana: window_size must be positive");
@@ -299,7 +306,7 @@ extern "C" int svsb200_build_vamana(const void* vectors, int dtype, size_t n, si
             rc = set_error("svsb200_build_vamana: window_size too large for shared memory");
             goto done;
         }
-        const int op = metric == SVSB200_L2 ? OP_L2F : OP_IPF;
+        const int op = metric == SVSB200_L2 ? OP_L2F : metric == SVSB200_IP ? OP_IPF : OP_COSF;
 
         BuildParams bp{};
         bp.hist = d_hist;
@@ -328,9 +335,9 @@ extern "C" int svsb200_build_vamana(const void* vectors, int dtype, size_t n, si
                 const uint32_t B = uint32_t(stop - start);
                 // 1. generate_neighbors: search ...
                 if (dtype == SVSB200_F32)
-                    batch_queries_kernel<SVSB200_F32><<<(B + 7) / 8, 256, 0, stream>>>(d_vectors, row_stride, uint32_t(dim), qstride, uint32_t(start), B, d_qf);
+                    batch_queries_kernel<SVSB200_F32><<<(B + 7) / 8, 256, 0, stream>>>(d_vectors, row_stride, uint32_t(dim), qstride, uint32_t(start), B, d_qf, d_qaux);
                 else
-                    batch_queries_kernel<SVSB200_F16><<<(B + 7) / 8, 256, 0, stream>>>(d_vectors, row_stride, uint32_t(dim), qstride, uint32_t(start), B, d_qf);
+                    batch_queries_kernel<SVSB200_F16><<<(B + 7) / 8, 256, 0, stream>>>(d_vectors, row_stride, uint32_t(dim), qstride, uint32_t(start), B, d_qf, d_qaux);
                 count_launch();
                 BUILD_TRY(cudaMemsetAsync(d_work, 0, 4, stream));
                 p.nq = B;

@@ -7,6 +7,7 @@ template <> cudaError_t launch_build_search<SVSB200_F32>(int op, const SearchPar
     switch (op) {
         case OP_L2F: return launch_fast_dims<SVSB200_F32, OP_L2F, true>(p, cfg);
         case OP_IPF: return launch_fast_dims<SVSB200_F32, OP_IPF, true>(p, cfg);
+        case OP_COSF: return launch_fast_dims<SVSB200_F32, OP_COSF, true>(p, cfg);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -15,6 +16,7 @@ template <> cudaError_t launch_build_prune_op<SVSB200_F32>(int op, const SearchP
     switch (op) {
         case OP_L2F: return launch_build_prune<SVSB200_F32, OP_L2F>(p, bp, grid, stream);
         case OP_IPF: return launch_build_prune<SVSB200_F32, OP_IPF>(p, bp, grid, stream);
+        case OP_COSF: return launch_build_prune<SVSB200_F32, OP_COSF>(p, bp, grid, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -57,9 +57,11 @@ __host__ __device__ inline size_t build_smem_bytes(uint32_t qstride) {
 
 // Row `id` of the dataset as the fp32 operand the distance code expects in q_s (what prepare_queries_kernel
 // does for a query: exact conversion, zero padding).
+// Returns the row's Euclidean norm (the `a_norm` of CosineSimilarity::fix_argument, cosine.h:117-119).
 template <int ROWT>
-__device__ __forceinline__ void stage_row(const SearchParams& p, uint32_t id, float* q_s, int lane) {
+__device__ __forceinline__ float stage_row(const SearchParams& p, uint32_t id, float* q_s, int lane) {
     const char* row = reinterpret_cast<const char*>(p.vectors) + size_t(id) * p.row_stride;
+    float sq = 0.f;
     for (uint32_t i = lane; i < p.qstride; i += 32) {
         float v = 0.f;
         if (i < p.dim) {
@@ -67,7 +69,10 @@ __device__ __forceinline__ void stage_row(const SearchParams& p, uint32_t id, fl
             else v = __half2float(reinterpret_cast<const __half*>(row)[i]);
         }
         q_s[i] = v;
+        sq = fmaf(v, v, sq);
     }
+    for (int o = 16; o; o >>= 1) sq += __shfl_xor_sync(0xFFFFFFFFu, sq, o);
+    return sqrtf(sq);
 }
 
 template <int ROWT, int OP, int DS, int KS>
@@ -104,9 +109,11 @@ __global__ void __launch_bounds__(32, 16) build_prune_kernel(const __grid_consta
         // ---- candidate pool ----
         uint32_t P = 0;       // entries whose key is known
         uint32_t M = 0;       // entries of lid[] whose distance to `node` still has to be computed
+        float qnorm = 1.0f;   // cosine: norm of the vector currently staged as the query
         if (!bp.reverse) {
             // the node as a query: prepared by the search launch of this round
             for (uint32_t i = lane; i < p.qstride; i += 32) q_s[i] = p.qf[size_t(w) * p.qstride + i];
+            qnorm = p.qaux[2 * size_t(w)];
             P = min(bp.hist_count[w], min(bp.hist_cap, kPoolMax));
             for (uint32_t i = lane; i < P; i += 32) {
                 const uint2 e = bp.hist[size_t(w) * bp.hist_cap + i];
@@ -125,7 +132,7 @@ __global__ void __launch_bounds__(32, 16) build_prune_kernel(const __grid_consta
                 M = min(M + __popc(m), kPoolMax - P);
             }
         } else {
-            stage_row<ROWT>(p, node, q_s, lane);
+            qnorm = stage_row<ROWT>(p, node, q_s, lane);
             // overflow edges of this round (vamana_build.h:528-531), walked by one lane
             if (lane == 0) {
                 uint32_t c = 0;
@@ -155,7 +162,7 @@ __global__ void __launch_bounds__(32, 16) build_prune_kernel(const __grid_consta
         __syncwarp();
         // distances node -> lid[0..M), appended to the pool
         for (uint32_t base = 0; base < M; base += 2 * GROUPS)
-            eval_pass<ROWT, OP, DS, 2, KS, true>(p, q_s, vectors, lid, lkey, base, M, g, t, 0.f, 0.f, ksign);
+            eval_pass<ROWT, OP, DS, 2, KS, true>(p, q_s, vectors, lid, lkey, base, M, g, t, qnorm, 0.f, ksign);
         __syncwarp();
         for (uint32_t i = lane; i < M; i += 32) {
             cid[P + i] = lid[i];
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(32, 16) build_prune_kernel(const __grid_consta
                     res[nres] = cid[j];
                 }
                 ++nres;
-                stage_row<ROWT>(p, cid[j], q_s, lane);
+                qnorm = stage_row<ROWT>(p, cid[j], q_s, lane);
                 __syncwarp();
                 // the later entries still available at this level, compacted
                 uint32_t L = 0;
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(32, 16) build_prune_kernel(const __grid_consta
                 if (L == 0) continue;
                 // djk for every listed entry: key(selected, candidate)
                 for (uint32_t base = 0; base < L; base += 2 * GROUPS)
-                    eval_pass<ROWT, OP, DS, 2, KS, true>(p, q_s, vectors, lid, lkey, base, L, g, t, 0.f, 0.f, ksign);
+                    eval_pass<ROWT, OP, DS, 2, KS, true>(p, q_s, vectors, lid, lkey, base, L, g, t, qnorm, 0.f, ksign);
                 __syncwarp();
                 for (uint32_t i = lane; i < L; i += 32) {
                     const uint32_t tt = lpos[i];

@@ -23,18 +23,18 @@ def _structural(graph, n, R):
 
 def _recall(data, graph, ep, queries, gt, metric, window):
     from scalablevectorsearch_b200 import DistanceType, SearchBufferConfig, Vamana
-    index = Vamana.from_arrays(data, graph, ep, {"l2": DistanceType.L2, "ip": DistanceType.MIP}[metric])
+    index = Vamana.from_arrays(data, graph, ep, {"l2": DistanceType.L2, "ip": DistanceType.MIP, "cosine": DistanceType.Cosine}[metric])
     index.search_parameters.buffer_config = SearchBufferConfig(window)
     ids, _ = index.search(queries, 10)
     return recall_at_k(ids, gt)
 
 
-@pytest.mark.parametrize("metric", ["l2", "ip"])
+@pytest.mark.parametrize("metric", ["l2", "ip", "cosine"])
 def test_build_on_reference_dataset_matches_reference_builder_recall(dataset, reflib, metric):
     """data/test_dataset (10k x 128), the reference's own build test shape (index_build.cpp: R=64... here R=32,
     window 64 to keep the CPU side quick)."""
     from scalablevectorsearch_b200 import DistanceType, VamanaBuildParameters, build_graph
-    dist = {"l2": DistanceType.L2, "ip": DistanceType.MIP}[metric]
+    dist = {"l2": DistanceType.L2, "ip": DistanceType.MIP, "cosine": DistanceType.Cosine}[metric]
     alpha = 1.2 if metric == "l2" else 0.95
     params = VamanaBuildParameters(alpha=alpha, graph_max_degree=32, window_size=64)
     g_gpu, ep_gpu = build_graph(dataset.data, dist, params)
