@@ -1833,8 +1833,22 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
     }
-    uint32_t nsplit = (2u * uint32_t(rep->sm_count) + mtiles - 1) / mtiles;
-    nsplit = std::max(1u, std::min(std::min(nsplit, 15u), ntiles));
+    // base ranges per query tile: at least two CTAs per SM's worth of work items, and among the admissible counts the
+    // one that wastes the least of the last wave (one CTA per SM: the grid runs in waves of sm_count)
+    uint32_t nsplit = 1;
+    {
+        const uint32_t sms = uint32_t(rep->sm_count), hi = std::min(15u, ntiles);
+        const uint32_t lo = std::max(1u, std::min(hi, (2u * sms + mtiles - 1) / mtiles));
+        double best = 1e30;
+        for (uint32_t c = lo; c <= hi; ++c) {
+            const uint32_t ctas = mtiles * c, waves = (ctas + sms - 1) / sms;
+            const double waste = double(waves) * sms / ctas + 0.01 * c;   // (slight preference for fewer candidates)
+            if (waste < best) {
+                best = waste;
+                nsplit = c;
+            }
+        }
+    }
     const size_t qrow = size_t(dim) * esize(qdtype);
     CUDA_TRY(sc->flat_a.ensure(size_t(mtiles) * 128 * KB * 32 * 2));
     CUDA_TRY(sc->flat_qnorm.ensure(size_t(mtiles) * 128));
