@@ -35,6 +35,21 @@ def _oracle_search(data, graph, ep, window):
     return run
 
 
+def _oracle_search_into(data, graph, ep, window, id_dtype):
+    """The same, through the `out=` protocol the CUDA local search uses (rows written straight into the rank's block)."""
+    plain = _oracle_search(data, graph, ep, window)
+
+    def run(q, k, out=None):
+        ids, d = plain(q, k)
+        if out is None:
+            return ids.to(id_dtype), d
+        out[0].copy_(ids.to(id_dtype))
+        out[1].copy_(d)
+        return out
+    run.takes_out = True
+    return run
+
+
 def _worker(rank, world, port, out_dir):
     import sys
     sys.path.insert(0, ROOT)
@@ -47,6 +62,10 @@ def _worker(rank, world, port, out_dir):
     q = torch.from_numpy(ds.queries[:101])          # odd count: unequal shards
     # Mode A: replicas
     a_ids, a_d = ReplicatedSearch(_oracle_search(ds.data, ds.graph, ds.entry_point, 20)).search(q, 10)
+    # the packed single-collective path with 4-byte ids, local rows written in place
+    a32_ids, a32_d = ReplicatedSearch(_oracle_search_into(ds.data, ds.graph, ds.entry_point, 20, torch.int32),
+                                      id_dtype=torch.int32).search(q, 10)
+    assert a32_ids.dtype == torch.int32 and torch.equal(a32_ids.to(torch.int64), a_ids) and torch.equal(a32_d, a_d)
     # Mode B: each rank owns half of the base vectors with its own (sub)graph
     n = ds.data.shape[0]
     lo, hi = (0, n // 2) if rank == 0 else (n // 2, n)
