@@ -88,6 +88,11 @@ int svsb200_index_assemble(
  * raw text of `table.key` into `out`. */
 int svsb200_toml_get(const char* path, const char* dotted_key, char* out, size_t capacity);
 
+/* Several entry points: VamanaIndex keeps a vector of them (include/svs/index/vamana/index.h:304-312) and
+ * EntryPointInitializer pushes every one before the walk starts (index/vamana/greedy_search.h:62-94).  1..32 distinct
+ * ids; the first replaces the entry point given at creation. */
+int svsb200_set_entry_points(svsb200_index* index, const uint32_t* entry_points, size_t count);
+
 int svsb200_index_destroy(svsb200_index* index);
 
 /* Introspection used by the host-side mirror (size()/dimensions()/get_graph_max_degree,

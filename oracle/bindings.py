@@ -56,6 +56,14 @@ class _Index:
 
     __del__ = close
 
+    def set_entry_points(self, entry_points):
+        """Several distinct entry points (oracle only; the compiled reference takes one)."""
+        eps = np.ascontiguousarray(entry_points, dtype=np.uint32)
+        fn = getattr(self._lib, f"{self._p}_index_set_entry_points")
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        if fn(self._h, eps.ctypes.data, len(eps)):
+            raise RuntimeError("set_entry_points failed")
+
     def set_threads(self, n: int):
         fn = getattr(self._lib, f"{self._p}_index_set_threads", None)
         if fn is not None:

@@ -432,6 +432,8 @@ typedef struct {
     void* data;      /* owned copy, row-major */
     uint32_t* graph; /* owned copy, n x (max_degree + 1) */
     uint32_t entry_point;
+    uint32_t entry_points[32]; /* index/vamana/index.h:304-312 holds a vector of entry points */
+    uint32_t n_entry;
     float scale, bias;
     int lvq;
     size_t row_stride, lvq_const_offset; /* row_stride 0 = dense */
@@ -445,11 +447,25 @@ static void greedy_search(const Index* ix, FixedQuery* f, const void* query, Buf
     fix_argument(f, query); /* :140 */
     buffer_clear(buf);      /* :79 */
     {
-        uint32_t id = ix->entry_point;
-        Entry e = {id, compute_distance(f, (const char*)ix->data + (size_t)id * row_bytes), 0};
-        buffer_push_back(buf, e);
-        if (evals) ++*evals;
-        /* buffer.sort(): a single entry point, nothing to order (:89). */
+        /* EntryPointInitializer (:62-94): push_back every entry point, then buffer.sort().  With one entry point
+         * there is nothing to order; with several (distinct ones) the sort is restated as a stable insertion sort
+         * by the comparator -- std::sort leaves the order of exactly tied distances unspecified. */
+        uint32_t ne = ix->n_entry > 1 ? ix->n_entry : 1;
+        for (uint32_t i = 0; i < ne; ++i) {
+            uint32_t id = ix->n_entry > 1 ? ix->entry_points[i] : ix->entry_point;
+            Entry e = {id, compute_distance(f, (const char*)ix->data + (size_t)id * row_bytes), 0};
+            buffer_push_back(buf, e);
+            if (evals) ++*evals;
+        }
+        for (size_t i = 1; i < buf->size; ++i) {
+            Entry x = buf->e[i];
+            size_t j = i;
+            while (j > 0 && cmp(buf, x.dist, buf->e[j - 1].dist)) {
+                buf->e[j] = buf->e[j - 1];
+                --j;
+            }
+            buf->e[j] = x;
+        }
     }
     while (!buffer_done(buf)) { /* :153 */
         Entry node = buffer_next(buf);

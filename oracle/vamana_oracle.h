@@ -38,6 +38,8 @@ size_t oracle_lvq8_row_stride(size_t dim);
 int oracle_lvq8_compress(const float* data, size_t n, size_t dim, const float* mean, void* out_rows);
 void* oracle_lvq8_index_create(const void* rows, size_t n, size_t dim, const float* mean,
                                const uint32_t* graph_rows, size_t max_degree, uint32_t entry_point, int metric);
+/* Several (distinct) entry points, as VamanaIndex::entry_point_ allows (index/vamana/index.h:304-312). */
+int oracle_index_set_entry_points(void* index, const uint32_t* entry_points, size_t count);
 void oracle_index_destroy(void* index);
 int oracle_index_search(void* index, int qtype, const void* queries, size_t nq, size_t k,
                         size_t window, size_t capacity, int visited_set, uint64_t* ids,

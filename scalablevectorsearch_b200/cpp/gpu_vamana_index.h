@@ -83,8 +83,8 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
                                             const auto& data,
                                             const auto& /*distance*/,
                                             auto entry_points) {
-            if (entry_points.size() != 1) {
-                throw ANNEXCEPTION("GpuVamanaIndex needs exactly one entry point");
+            if (entry_points.empty() || entry_points.size() > 32) {
+                throw ANNEXCEPTION("GpuVamanaIndex takes 1 to 32 entry points");
             }
             const auto& rows = graph.get_data(); // uint32[n][max_degree + 1], degree first
             svsb200_index* raw = nullptr;
@@ -127,6 +127,10 @@ class GpuVamanaIndex : public svs::index::vamana::VamanaIndex<Graph, Data, Dist>
                 ));
             }
             handle_.reset(raw, detail::HandleDeleter{});
+            if (entry_points.size() > 1) {   // index.h:304-312: every entry point seeds the walk
+                std::vector<uint32_t> eps(entry_points.begin(), entry_points.end());
+                detail::check(svsb200_set_entry_points(raw, eps.data(), eps.size()));
+            }
         });
     }
 

@@ -38,6 +38,8 @@ struct SearchParams {
     uint32_t lvq_const_offset;  // LVQ-8: byte offset of {delta, lower} (2 x f16) inside a row
     uint32_t gstride;
     uint32_t entry_point;
+    const uint32_t* entry_points;   // more than one entry point (index/vamana/index.h:304-312 holds a vector): device array
+    uint32_t n_entry;               // 0 or 1: `entry_point` alone
     // distance post-processing
     int greater;               // comparator std::greater (IP / cosine): keys are negated
     int sq;                    // rows are scalar-quantised codes

@@ -95,7 +95,8 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
         for (uint32_t i = lane; i < fsets; i += 32) filt[i] = make_uint4(NONE, NONE, NONE, NONE);
         // ---- EntryPointInitializer (greedy_search.h:62-94): the entry point goes through the same
         // evaluate-and-merge code as a hop's neighbours, into the empty buffer ----
-        uint32_t size = 0, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
+        const uint32_t E = p.n_entry > 1 ? min(p.n_entry, 32u) : 1u;   // entry points (index/vamana/index.h:304-312)
+        uint32_t size = 0, cursor = 0, n_hops = 0, n_evals = E, n_fetched = E;
         uint32_t n_hist = 0;
         uint32_t staged_node = NONE;          // node whose adjacency row sits in nxt[]
         uint32_t nxt[kFastMaxGW];
@@ -111,8 +112,8 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             uint32_t ncand = 0;
             if (first) {
                 first = 0;
-                if (lane == 0) cid[0] = p.entry_point;
-                ncand = 1;
+                if (uint32_t(lane) < E) cid[lane] = E > 1 ? p.entry_points[lane] : p.entry_point;
+                ncand = E;
                 __syncwarp();
             } else {
             // buffer.next(): first unvisited entry inside min(size, window)

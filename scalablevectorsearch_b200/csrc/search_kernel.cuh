@@ -641,16 +641,38 @@ __global__ void __launch_bounds__(256, SVSB200_MIN_BLOCKS) vamana_search_kernel(
         __syncwarp();
 
         // ---- EntryPointInitializer (greedy_search.h:62-94): clear, push entry point ----
-        uint32_t size = EXH ? 0 : 1, cursor = 0, n_hops = 0, n_evals = 1, n_fetched = 1;
+        const uint32_t E = p.n_entry > 1 ? min(p.n_entry, p.deg_pad) : 1u;
+        uint32_t size = EXH ? 0 : 1, cursor = 0, n_hops = 0, n_evals = E, n_fetched = E;
         if constexpr (!EXH) {
-            if (lane == 0) cid[0] = p.entry_point;
+            for (uint32_t i = lane; i < E; i += 32) cid[i] = E > 1 ? p.entry_points[i] : p.entry_point;
             __syncwarp();
-            eval_pass<ROWT, OP, DS, 1, KS>(p, q_s, vectors, cid, ckey, 0, 1, g, t, aux0, aux1, ksign);
+            for (uint32_t base = 0; base < E; base += GROUPS)
+                eval_pass<ROWT, OP, DS, 1, KS>(p, q_s, vectors, cid, ckey, base, E, g, t, aux0, aux1, ksign);
             __syncwarp();
             if (lane == 0) {
-                bkey[0] = ckey[0];
-                bid[0] = p.entry_point;
+                // push_back every entry point, then sort (greedy_search.h:80-92); here: insertion in entry order
+                // (ties keep that order, a repeated id is dropped, the list is cut at the capacity)
+                size = 0;
+                for (uint32_t i = 0; i < E; ++i) {
+                    const float d = ckey[i];
+                    const uint32_t id = cid[i];
+                    bool dup = false;
+                    for (uint32_t j = 0; j < size; ++j) dup |= bid[j] == id;
+                    if (dup) continue;
+                    uint32_t pos = size;
+                    while (pos > 0 && d < bkey[pos - 1]) --pos;
+                    if (pos >= C) continue;
+                    const uint32_t last = min(size, C - 1);
+                    for (uint32_t j = last; j > pos; --j) {
+                        bkey[j] = bkey[j - 1];
+                        bid[j] = bid[j - 1];
+                    }
+                    bkey[pos] = d;
+                    bid[pos] = id;
+                    size = min(size + 1, C);
+                }
             }
+            size = __shfl_sync(FULL, size, 0);
             __syncwarp();
         }
         uint32_t scan_base = exh_lo;   // EXH: first id of the current block

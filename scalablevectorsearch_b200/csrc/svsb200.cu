@@ -118,6 +118,7 @@ struct Replica {
     uint32_t* d_graph = nullptr;
     uint16_t* d_ref_degree = nullptr;
     float* d_mean = nullptr;          // LVQ-8: dataset mean
+    uint32_t* d_entry = nullptr;      // entry points when there are several
     // tensor-core flat search: the base vectors as fp16 UMMA tiles + per-row bias, built on first use
     void* flat_b = nullptr;
     float* flat_bias = nullptr;
@@ -133,6 +134,7 @@ struct Replica {
         if (d_graph) cudaFree(d_graph);
         if (d_ref_degree) cudaFree(d_ref_degree);
         if (d_mean) cudaFree(d_mean);
+        if (d_entry) cudaFree(d_entry);
         if (flat_b) cudaFree(flat_b);
         if (flat_bias) cudaFree(flat_bias);
         if (flat_xmax) cudaFree(flat_xmax);
@@ -151,6 +153,7 @@ struct svsb200_index {
     uint32_t lvq_const_offset = 0;
     size_t device_bytes = 0;          // per replica
     uint64_t id_offset = 0;           // added to every 64-bit output id (shard of a larger index)
+    uint32_t n_entry = 1;             // entry points (the first one is `entry_point`)
     long cfg_window = 0, cfg_capacity = 0, cfg_visited = 0;   // search parameters of the TOML an index was assembled from
     std::vector<std::unique_ptr<Replica>> reps;
     int counting = 0;
@@ -1060,6 +1063,22 @@ int svsb200_set_counting(svsb200_index* ix, int enabled) {
     return 0;
 }
 
+int svsb200_set_entry_points(svsb200_index* ix, const uint32_t* entry_points, size_t count) {
+    if (!ix || !entry_points) return fail("svsb200_set_entry_points: NULL argument");
+    if (count == 0 || count > 32) return fail("svsb200_set_entry_points: 1..32 entry points");
+    for (size_t i = 0; i < count; ++i)
+        if (entry_points[i] >= ix->n) return fail("svsb200_set_entry_points: entry point out of range");
+    for (auto& rep : ix->reps) {
+        CUDA_TRY(cudaSetDevice(rep->device));
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (!rep->d_entry) CUDA_TRY(cudaMalloc(&rep->d_entry, 32 * sizeof(uint32_t)));
+        CUDA_TRY(cudaMemcpy(rep->d_entry, entry_points, count * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
+    ix->entry_point = entry_points[0];
+    ix->n_entry = uint32_t(count);
+    return 0;
+}
+
 int svsb200_set_id_offset(svsb200_index* ix, uint64_t offset) {
     if (!ix) return fail("svsb200_set_id_offset: NULL index");
     ix->id_offset = offset;
@@ -1205,6 +1224,8 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     p.row_stride = ix->row_stride;
     p.gstride = ix->gstride;
     p.entry_point = ix->entry_point;
+    p.entry_points = rep->d_entry;
+    p.n_entry = rep->d_entry ? ix->n_entry : 1;
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
     p.lvq = ix->storage == SVSB200_LVQ8;

@@ -438,6 +438,11 @@ class Vamana:
         _lib.check(self._lib.svsb200_last_kernel_ms(self._h, C.byref(ms)))
         return float(ms.value)
 
+    def set_entry_points(self, entry_points):
+        """Several distinct entry points (``VamanaIndex::entry_point_`` is a vector, index/vamana/index.h:304-312)."""
+        eps = np.ascontiguousarray(entry_points, dtype=np.uint32)
+        _lib.check(self._lib.svsb200_set_entry_points(self._h, eps.ctypes.data, len(eps)))
+
     def set_option(self, name: str, value: int):
         _lib.check(self._lib.svsb200_set_option(self._h, name.encode(), int(value)))
 

@@ -544,3 +544,20 @@ def test_runtime_abi_demo_program(tmp_path):
     assert rows["range"] and all(dist < radius for _, dist in rows["range"])
     label, dist = rows["get_distance"][0]
     assert label == rows["plain"][0][0] and dist == pytest.approx(rows["plain"][0][1], rel=1e-6)
+
+
+@pytest.mark.parametrize("metric", ["l2", "cosine"])
+def test_several_entry_points(dataset, oracle, metric):
+    """EntryPointInitializer pushes every entry point (greedy_search.h:62-94; index.h:304-312 holds a vector)."""
+    eps = [9426, 17, 4242, 9999, 5]
+    index = make_index(dataset.data, dataset.graph, eps[0], metric)
+    index.set_entry_points(eps)
+    want = oracle.index(dataset.data, dataset.graph, eps[0], metric)
+    want.set_entry_points(eps)
+    q = dataset.queries[:128]
+    for window, cap in ((3, 3), (20, 33), (64, 64)):
+        wi, wd = want.search(q, 3 if cap < 10 else 10, window, cap)
+        for generic in (0, 1):
+            index.set_option("generic_kernel", generic)
+            got = search(index, q, 3 if cap < 10 else 10, window, cap)
+            assert_same(got, wi, wd, f"{metric} eps w{window} generic{generic}")
