@@ -90,6 +90,7 @@ struct Scratch {
     int* d_cancel = nullptr;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_done = nullptr;
     bool timed = false;
+    bool poll_cancel = false;        // this search was given a cancellation predicate: the kernels poll the flag
     size_t counted_nq = 0;
     int last_kernel = 0;
     ~Scratch() {
@@ -1249,7 +1250,7 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     p.id_offset = id_bytes == 8 ? ix->id_offset : 0;
     p.out_dists = d_out_dists;
     p.work_counter = sc->d_counter;
-    p.cancel = sc->d_cancel;
+    p.cancel = sc->poll_cancel ? sc->d_cancel : nullptr;   // (no predicate: no per-hop poll in the kernel)
     p.hops = counting ? sc->hops.ptr : nullptr;
     p.evals = counting ? sc->evals.ptr : nullptr;
     p.fetched = counting ? sc->fetched.ptr : nullptr;
@@ -1454,6 +1455,7 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
         used_lo.push_back(lo);
         used_m.push_back(m);
         sc->timed = false;
+        sc->poll_cancel = cancel != nullptr;
         auto step = [&]() -> int {
             CUDA_TRY(sc->q_raw.ensure(m * qrow));
             CUDA_TRY(sc->ids.ensure(m * k * size_t(id_bytes)));
@@ -1485,8 +1487,10 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
         if (rc) first_error = g_error;
     }
     if (rc_wait == 0) rc_wait = wait_all(used);
-    for (size_t i = 0; i < used.size(); ++i)
+    for (size_t i = 0; i < used.size(); ++i) {
+        used[i]->poll_cancel = false;
         if (used_rep[i]) release(used_rep[i], used[i]);
+    }
     if (rc) {
         g_error = first_error;
         return rc;

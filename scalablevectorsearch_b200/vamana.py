@@ -393,7 +393,7 @@ class Vamana:
         dd = np.ctypeslib.as_array(C.cast(pd, C.POINTER(C.c_float)), shape=(max(total, 1),))[:total].copy()
         self._lib.svsb200_free(pi)
         self._lib.svsb200_free(pd)
-        offs = np.concatenate([[0], np.cumsum(counts)])
+        offs = np.concatenate([[0], np.cumsum(counts.astype(np.int64))])
         return [(ids[offs[i]:offs[i + 1]], dd[offs[i]:offs[i + 1]]) for i in range(nq)]
 
     def flat_search(self, queries: np.ndarray, n_neighbors: int):
