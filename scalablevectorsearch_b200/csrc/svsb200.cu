@@ -1858,18 +1858,22 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
     }
-    // base ranges per query tile: at least two CTAs per SM's worth of work items, and among the admissible counts the
-    // one that wastes the least of the last wave (one CTA per SM: the grid runs in waves of sm_count)
+    // Base ranges per query tile, from a cost model of the kernel (measured, profiles/flat_r2.json): a CTA's tile
+    // takes max(MMA time, epilogue time); the epilogue pays ~150 instructions per list update, and a query sees
+    // KC ln(rows_in_range / KC) updates per range -- so more ranges mean more updates, fewer ranges fewer CTAs
+    // (one CTA per SM: the grid runs in waves of sm_count).
     uint32_t nsplit = 1;
     {
-        const uint32_t sms = uint32_t(rep->sm_count), hi = std::min(15u, ntiles);
-        const uint32_t lo = std::max(1u, std::min(hi, (2u * sms + mtiles - 1) / mtiles));
-        double best = 1e30;
-        for (uint32_t c = lo; c <= hi; ++c) {
-            const uint32_t ctas = mtiles * c, waves = (ctas + sms - 1) / sms;
-            const double waste = double(waves) * sms / ctas + 0.01 * c;   // (slight preference for fewer candidates)
-            if (waste < best) {
-                best = waste;
+        const double kc = double(flat_kc()), sms = double(rep->sm_count);
+        double best = 1e300;
+        for (uint32_t c = 1; c <= std::min(15u, ntiles); ++c) {
+            const double rows = double(n) / c, tiles_per_cta = double(ntiles) / c;
+            const double updates_per_warp_tile = 32.0 * kc * std::max(1.0, std::log(rows / kc)) / tiles_per_cta;
+            const double tile_cycles = std::max(270.0 * KB, 3.0 * (600.0 + 150.0 * updates_per_warp_tile));
+            const double waves = std::ceil(double(mtiles) * c / sms);
+            const double cost = waves * tiles_per_cta * tile_cycles;
+            if (cost < best) {
+                best = cost;
                 nsplit = c;
             }
         }
