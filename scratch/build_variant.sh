@@ -9,6 +9,6 @@ for f in svsb200 search_f32 search_f16 search_i8 search_u8 search_lvq8 fast_f32 
   ( /usr/local/cuda/bin/nvcc $FLAGS -c $f.cu -o $OUT/$f.o ) &
 done
 wait
-/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scratch/variants/libsvsb200_$NAME.so $OUT/*.o
+/usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../scratch/variants/libsvsb200_$NAME.so $OUT/*.o build.o build_f32.o build_f16.o flat.o
 rm -rf $OUT
 echo built libsvsb200_$NAME.so

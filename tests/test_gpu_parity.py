@@ -540,7 +540,7 @@ def test_runtime_abi_demo_program(tmp_path):
     assert np.all(even % 2 == 0)
     gt_even = np.argsort(np.where(np.arange(n)[None, :] % 2 == 0, d, np.inf), axis=1)[:, :k]
     assert np.mean([len(set(even[i]) & set(gt_even[i])) for i in range(nq)]) / k > 0.85
-    radius = rows["plain"][k - 1][1]
+    radius = rows["even"][k - 1][1]  # the demo passes the filtered search's k-th distance of query 0
     assert rows["range"] and all(dist < radius for _, dist in rows["range"])
     label, dist = rows["get_distance"][0]
     assert label == rows["plain"][0][0] and dist == pytest.approx(rows["plain"][0][1], rel=1e-6)
