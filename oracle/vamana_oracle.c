@@ -611,6 +611,30 @@ void* oracle_lvq8_index_create(const void* rows, size_t n, size_t dim, const flo
     return ix;
 }
 
+/* index/vamana/index.h:304-312: the index holds a vector of entry points; all of them start a search. */
+int oracle_index_set_entry_points(void* h, const uint32_t* entry_points, size_t count) {
+    Index* ix = (Index*)h;
+    if (!ix || !entry_points || count == 0 || count > 32) {
+        snprintf(g_error, sizeof(g_error), "between 1 and 32 entry points");
+        return -1;
+    }
+    for (size_t i = 0; i < count; ++i) {
+        if (entry_points[i] >= ix->n) {
+            snprintf(g_error, sizeof(g_error), "entry point out of range");
+            return -1;
+        }
+        for (size_t j = 0; j < i; ++j)
+            if (entry_points[j] == entry_points[i]) {
+                snprintf(g_error, sizeof(g_error), "entry points must be distinct");
+                return -1;
+            }
+    }
+    memcpy(ix->entry_points, entry_points, count * sizeof(uint32_t));
+    ix->n_entry = (uint32_t)count;
+    ix->entry_point = entry_points[0];
+    return 0;
+}
+
 void oracle_index_destroy(void* h) {
     Index* ix = (Index*)h;
     if (!ix) return;

@@ -94,33 +94,36 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
 // Instruction descriptor (InstrDescriptor): D = F32, A = B = F16, both K-major, N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t kFlatIdesc = (1u << 4) | ((FLAT_BN >> 3) << 17) | ((FLAT_BM >> 4) << 24);
 
-// Per-query list of the FLAT_KC smallest keys (shared memory, entry-major so that a warp's accesses are conflict
-// free).  State = {count, threshold}: the threshold is +inf until the list is full, then its maximum.
-__device__ __noinline__ uint64_t flat_list_insert(float* lkey, uint32_t* lid, uint32_t row, uint64_t st, float key, uint32_t id) {
-    uint32_t count = uint32_t(st >> 32);
-    if (count < FLAT_KC) {
-        lkey[count * FLAT_BM + row] = key;
-        lid[count * FLAT_BM + row] = id;
-        ++count;
-    } else {
-        uint32_t arg = 0;   // replace the current maximum
-        float mx = lkey[row];
-        for (uint32_t e = 1; e < FLAT_KC; ++e) {
-            const float ke = lkey[e * FLAT_BM + row];
-            if (ke > mx) {
-                mx = ke;
-                arg = e;
-            }
-        }
-        lkey[arg * FLAT_BM + row] = key;
-        lid[arg * FLAT_BM + row] = id;
+// Per-query list of the FLAT_KC smallest keys: shared memory, [query row][FLAT_KC] with FLAT_KC odd, so that both a
+// lane walking its own row and a warp reading one row side by side are bank-conflict free.  Keys are stored as
+// order-preserving unsigned integers (REDUX.MAX works on them); a list starts full of +inf / no-id entries, so there
+// is no fill count -- an update always replaces the current maximum, and the row's threshold is the new maximum.
+static_assert(FLAT_KC % 2 == 1 && FLAT_KC > 32 && FLAT_KC <= 64, "list layout");
+__device__ __forceinline__ uint32_t flat_ord(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return u ^ (uint32_t(int32_t(u) >> 31) | 0x80000000u);
+}
+__device__ __forceinline__ float flat_unord(uint32_t o) {
+    return __uint_as_float(o ^ ((o >> 31) ? 0x80000000u : 0xFFFFFFFFu));
+}
+// The whole warp updates the list of row `warp_row0 + src` with (key, id) broadcast from lane `src`; returns the row's
+// new threshold (warp-uniform).
+__device__ __forceinline__ float flat_list_replace_max(uint32_t* lkey, uint32_t* lid, uint32_t list_row, uint32_t lane,
+                                                      float key, uint32_t id) {
+    uint32_t* rk = lkey + list_row * FLAT_KC;
+    uint32_t v0 = rk[lane];
+    uint32_t v1 = lane + 32 < FLAT_KC ? rk[lane + 32] : 0u;
+    const uint32_t mx = __reduce_max_sync(0xFFFFFFFFu, max(v0, v1));
+    const uint32_t in0 = __ballot_sync(0xFFFFFFFFu, v0 == mx);
+    const uint32_t in1 = __ballot_sync(0xFFFFFFFFu, v1 == mx && lane + 32 < FLAT_KC);
+    const uint32_t slot = in0 ? uint32_t(__ffs(int(in0)) - 1) : uint32_t(__ffs(int(in1)) + 31);
+    const uint32_t nk = flat_ord(key);
+    if (lane == (slot & 31u)) {
+        rk[slot] = nk;
+        lid[list_row * FLAT_KC + slot] = id;
+        if (slot < 32) v0 = nk; else v1 = nk;
     }
-    float thr = INFINITY;
-    if (count == FLAT_KC) {
-        thr = lkey[row];
-        for (uint32_t e = 1; e < FLAT_KC; ++e) thr = fmaxf(thr, lkey[e * FLAT_BM + row]);
-    }
-    return (uint64_t(count) << 32) | __float_as_uint(thr);
+    return flat_unord(__reduce_max_sync(0xFFFFFFFFu, max(v0, v1)));
 }
 
 struct FlatParams {
@@ -140,8 +143,8 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stages = smem;
     float* bias_s = reinterpret_cast<float*>(smem + size_t(FLAT_STAGES) * FLAT_STAGE_BYTES);   // [2][FLAT_BN]
-    float* lkey = bias_s + 2 * FLAT_BN;                                                         // [KC][128]
-    uint32_t* lid = reinterpret_cast<uint32_t*>(lkey + size_t(FLAT_KC) * FLAT_BM);
+    uint32_t* lkey = reinterpret_cast<uint32_t*>(bias_s + 2 * FLAT_BN);                         // [128][KC] ordered keys
+    uint32_t* lid = lkey + size_t(FLAT_KC) * FLAT_BM;
     uint64_t* bars = reinterpret_cast<uint64_t*>(lid + size_t(FLAT_KC) * FLAT_BM);
     uint64_t* full = bars;                       // [STAGES] bytes of a stage have landed
     uint64_t* empty = bars + FLAT_STAGES;        // [STAGES] the MMAs reading a stage have completed
@@ -234,7 +237,12 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
         const uint32_t quad = warp & 3u;
         const uint32_t row = quad * 32 + lane;
         uint32_t acc = 0, aph = 0;
-        uint64_t st = uint64_t(__float_as_uint(INFINITY));   // {entries in the list, threshold bits}
+        float thr = INFINITY;   // this row's threshold: the largest key of its list
+        for (uint32_t e = 0; e < FLAT_KC; ++e) {
+            lkey[row * FLAT_KC + e] = flat_ord(INFINITY);
+            lid[row * FLAT_KC + e] = 0xFFFFFFFFu;
+        }
+        __syncwarp();
         for (uint32_t nt = nt_lo; nt < nt_hi; ++nt) {
             mbar_wait(tmem_full + acc, aph);
             mbar_wait(bias_full + acc, aph);
@@ -266,11 +274,21 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                     key[4 * i4 + 3] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 3]), b4.w);
                     best = fminf(fminf(fminf(best, key[4 * i4 + 0]), fminf(key[4 * i4 + 1], key[4 * i4 + 2])), key[4 * i4 + 3]);
                 }
-                if (best < __uint_as_float(uint32_t(st))) {
+                // (warp-uniform branch; inside, one key at a time: the lanes whose key beats their row's threshold are
+                // served in turn by the whole warp)
+                if (__any_sync(0xFFFFFFFFu, best < thr)) {
 #pragma unroll
-                    for (uint32_t i = 0; i < 32; ++i)
-                        if (key[i] < __uint_as_float(uint32_t(st)))
-                            st = flat_list_insert(lkey, lid, row, st, key[i], nt * FLAT_BN + c * 32 + i);
+                    for (uint32_t i = 0; i < 32; ++i) {
+                        uint32_t hits = __ballot_sync(0xFFFFFFFFu, key[i] < thr);
+                        while (hits) {
+                            const uint32_t src = uint32_t(__ffs(int(hits)) - 1);
+                            hits &= hits - 1;
+                            const float k_src = __shfl_sync(0xFFFFFFFFu, key[i], src);
+                            const float t = flat_list_replace_max(lkey, lid, quad * 32 + src, lane, k_src,
+                                                                  nt * FLAT_BN + c * 32 + i);
+                            if (lane == src) thr = t;
+                        }
+                    }
                 }
             }
             tc_fence_before();
@@ -282,10 +300,10 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
         const size_t q = size_t(mtile) * FLAT_BM + row;
         float* ok = fp.cand_key + (q * fp.nsplit + split) * FLAT_KC;
         uint32_t* oi = fp.cand_id + (q * fp.nsplit + split) * FLAT_KC;
-        const uint32_t count = uint32_t(st >> 32);
+        __syncwarp();
         for (uint32_t e = 0; e < FLAT_KC; ++e) {
-            ok[e] = e < count ? lkey[e * FLAT_BM + row] : INFINITY;
-            oi[e] = e < count ? lid[e * FLAT_BM + row] : 0xFFFFFFFFu;
+            ok[e] = flat_unord(lkey[row * FLAT_KC + e]);
+            oi[e] = lid[row * FLAT_KC + e];
         }
     }
     tc_fence_before();

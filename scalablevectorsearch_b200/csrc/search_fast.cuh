@@ -237,33 +237,11 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 // lower_bound with !cmp(d, other) (search_buffer.h:364-371): number of entries that
                 // are better than or equal to d
                 uint32_t ipos = 0;
-#ifdef SVSB200_BSEARCH4
-                // 4-ary: three independent probes per step (their shared-memory latencies overlap), half the
-                // dependent steps of the binary search; `ipos` = number of entries e with !(d < e)
-                {
-                    uint32_t lo = 0, len = size;   // answer in [lo, lo + len]
-                    while (len > 0) {
-                        const uint32_t q1 = (len + 3) >> 2;               // probe stride
-                        const uint32_t p1 = lo + q1, p2 = lo + 2 * q1, p3 = lo + 3 * q1;
-                        const bool ok1 = p1 <= lo + len && !(d < __uint_as_float(buf[p1 - 1].x));
-                        const bool ok2 = p2 <= lo + len && !(d < __uint_as_float(buf[min(p2, size) - 1].x));
-                        const bool ok3 = p3 <= lo + len && !(d < __uint_as_float(buf[min(p3, size) - 1].x));
-                        // the predicate is monotone (sorted keys): ok3 => ok2 => ok1
-                        if (ok3) { lo = p3; len = len - 3 * q1; }
-                        else if (ok2) { lo = p2; len = q1 - 1; }
-                        else if (ok1) { lo = p1; len = q1 - 1; }
-                        else { len = q1 - 1; }
-                        if (!__any_sync(FULL, len > 0)) break;
-                    }
-                    ipos = lo;
-                }
-#else
 #pragma unroll 1
                 for (uint32_t step = size ? 1u << (31 - __clz(int(size))) : 0u; step; step >>= 1) {
                     const uint32_t j = ipos + step;
                     if (j <= size && !(d < __uint_as_float(buf[j - 1].x))) ipos = j;
                 }
-#endif
                 // duplicate-id scan over the equal-key run (search_buffer.h:380-391)
                 if (surv) {
                     uint32_t j = ipos;

@@ -53,3 +53,16 @@ def test_product_never_touches_the_oracle():
                     f"{os.path.join(dirpath, f)} mentions the oracle"
     out = os.popen(f"ldd {os.path.join(pkg, 'libsvsb200.so')}").read()
     assert "oracle" not in out and "svsref" not in out
+
+
+def test_oracle_library_exports_every_declared_symbol():
+    """The checker's own header and shared object must agree (a declared-but-undefined function only shows up when a
+    GPU test first calls it)."""
+    from oracle.bindings import OracleLib
+    OracleLib()   # builds oracle/liboracle.so on demand
+    header = open(os.path.join(ROOT, "oracle", "vamana_oracle.h")).read()
+    names = set(re.findall(r"\b(oracle_[a-z0-9_]+)\s*\(", header))
+    assert len(names) > 10
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing

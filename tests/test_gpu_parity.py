@@ -543,7 +543,7 @@ def test_runtime_abi_demo_program(tmp_path):
     radius = rows["even"][k - 1][1]  # the demo passes the filtered search's k-th distance of query 0
     assert rows["range"] and all(dist < radius for _, dist in rows["range"])
     label, dist = rows["get_distance"][0]
-    assert label == rows["plain"][0][0] and dist == pytest.approx(rows["plain"][0][1], rel=1e-6)
+    assert label == rows["even"][0][0] and dist == pytest.approx(rows["even"][0][1], rel=1e-6)   # l, d hold the filtered search
 
 
 @pytest.mark.parametrize("metric", ["l2", "cosine"])
