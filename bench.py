@@ -319,6 +319,8 @@ def run_ours(args):
     q_weak = queries if world == 1 else np.concatenate(
         [queries] + [clustered_queries(w["nq"], w["dim"], r) for r in range(1, world)])
 
+    kernel_kind = {}
+
     def time_mode(q_np):
         """W warm-ups, K timed steps of the device-resident multi-GPU search (local search -> one NCCL all-gather of
         the result rows), CUDA events on this rank's stream, max over ranks."""
@@ -342,6 +344,7 @@ def run_ours(args):
             searcher.search(q_dev, k)
             torch.cuda.synchronize()
             kern.append(index.last_kernel_ms())
+        kernel_kind["timed"] = index.get_option("last_kernel")
         t = torch.tensor([ms, float(np.mean(kern))], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -526,7 +529,7 @@ def run_ours(args):
             "recall_at_10": round(recall, 4),
             "ground_truth": ground_truth,
             "parallelism": f"replicas x{world}: queries split with threads::balance, one NCCL all-gather of the top-k rows",
-            "kernel": {1: "vamana_search_fast_kernel", 0: "vamana_search_kernel"}[index.get_option("last_kernel")],
+            "kernel": {1: "vamana_search_fast_kernel", 0: "vamana_search_kernel"}[kernel_kind["timed"]],
             "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "matches_device_path": same, "path": e2e_path},
             "gpu_launches": int(launches),
@@ -576,7 +579,10 @@ def run_sharded(args):
         dist.init_process_group("nccl", device_id=dev)
     barrier = (lambda: dist.barrier()) if world > 1 else (lambda: None)
     w = WORKLOADS[args.workload]
-    lo, hi = balance(w["n"], world, rank)
+    # --shards-total S > world: this run holds only the first `world` of S shards (rank r = shard r) -- one GPU's
+    # share of the S-GPU job, for sizing it; the line says so
+    total_shards = max(world, args.shards_total)
+    lo, hi = balance(w["n"], total_shards, rank)
     if w.get("per_shard_data"):
         from scalablevectorsearch_b200.synthetic import clustered_base_block, clustered_queries
         queries = clustered_queries(w["nq"], w["dim"], 0)
@@ -587,7 +593,9 @@ def run_sharded(args):
         del base
     shard = np.ascontiguousarray(shard.astype(np.float16 if w["dtype"] == "float16" else np.float32))
     ws = dict(w, n=hi - lo, build_share=world)
-    ep, graph = build_graph_cached(f"{args.workload}_shard{rank}of{world}", ws, shard, True, lambda: None)
+    t_build = time.time()
+    ep, graph = build_graph_cached(f"{args.workload}_shard{rank}of{total_shards}", ws, shard, True, lambda: None)
+    t_build = time.time() - t_build
     barrier()
     metric = {"l2": DistanceType.L2, "ip": DistanceType.MIP}[w["metric"]]
     index = Vamana.from_arrays(shard, graph, ep, metric, device=local_rank)
@@ -615,12 +623,23 @@ def run_sharded(args):
     r_ids, r_d = RefLib().index(shard, graph, ep, w["metric"], threads=max(1, effective_cpus() // world)).search(
         queries[:ns], k, w["window"], w["window"])
     r_ids = r_ids.astype(np.int64) + lo
-    parts = [None] * world
+    # exact top-k of the same sample on this shard (tensor-core flat search), for the recall of the merged result
+    gt_i = torch.empty((ns, k), dtype=torch.int64, device=dev)
+    gt_d = torch.empty((ns, k), dtype=torch.float32, device=dev)
+    index.flat_search_device(q_dev.data_ptr(), queries.dtype, ns, k, gt_i.data_ptr(), gt_d.data_ptr(),
+                             stream=torch.cuda.current_stream(dev).cuda_stream or 1)
+    torch.cuda.synchronize()
+    parts, gts = [None] * world, [None] * world
     if world > 1:
         dist.all_gather_object(parts, (r_ids, r_d))
+        dist.all_gather_object(gts, (gt_i.cpu().numpy() + lo, gt_d.cpu().numpy()))
     else:
-        parts = [(r_ids, r_d)]
+        parts, gts = [(r_ids, r_d)], [(gt_i.cpu().numpy() + lo, gt_d.cpu().numpy())]
     if rank == 0:
+        gt_ids, _ = merge_topk_reference_order(np.stack([g_[0] for g_ in gts]), np.stack([g_[1] for g_ in gts]), k,
+                                               w["metric"] != "l2")
+        got = ids[:ns].cpu().numpy()
+        recall = float(np.mean([len(set(got[i].tolist()) & set(gt_ids[i].tolist())) for i in range(ns)])) / k
         want_ids, want_d = merge_topk_reference_order(np.stack([p_[0] for p_ in parts]), np.stack([p_[1] for p_ in parts]), k,
                                                       w["metric"] != "l2")
         ok = bool(np.array_equal(want_ids, ids[:ns].cpu().numpy()) and np.array_equal(want_d, d[:ns].cpu().numpy()))
@@ -629,10 +648,13 @@ def run_sharded(args):
             "metric": "QPS", "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": float(t[0]) / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "n": w["n"], "shards": world, "dim": w["dim"], "base_dtype": w["dtype"],
+            "config": {"workload": args.workload, "n": w["n"], "shards": total_shards, "shards_in_this_run": world,
+                       "rows_per_shard": hi - lo, "graph_seconds_rank0": round(t_build, 1),
+                       "graph_builder": w.get("builder", "reference cpu"), "dim": w["dim"], "base_dtype": w["dtype"],
                        "distance": w["metric"], "batch": nq, "k": k, "search_window": w["window"],
                        "parallelism": f"index sharded x{world} (own graph per shard), NCCL all-gather + TotalOrder merge"},
-            "matches_reference_per_shard_plus_merge": ok, "checked_queries": ns}), flush=True)
+            "matches_reference_per_shard_plus_merge": ok, "checked_queries": ns, "recall_at_10": round(recall, 4)}),
+            flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -653,6 +675,8 @@ def main():
     ap.add_argument("--rows-in-flight", dest="rows_in_flight", type=int, default=0)
     ap.add_argument("--filter-slots", dest="filter_slots", type=int, default=-1)
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (svsb200_set_option)")
+    ap.add_argument("--shards-total", dest="shards_total", type=int, default=0,
+                    help="sharded workloads: split the base into this many shards and hold only the first --gpus of them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--weak", action="store_true",
                     help="reference arm only: label the line as the weak-scaling batch (our arm reports the strong "

@@ -161,6 +161,7 @@ struct svsb200_index {
     // options
     long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
     long generic_kernel = 0;          // 1: force the generic (round-1) kernel instead of the lean one
+    long host_chunks = 0;             // host-buffer searches: pieces per device whose copies overlap the kernels (0 = auto)
     std::mutex mu;
     Scratch* last = nullptr;          // scratch of the most recent search: counters, kernel time, kernel kind
 };
@@ -1104,6 +1105,9 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
         ix->filter_tag16 = value;
     } else if (key == "generic_kernel") {
         ix->generic_kernel = value;
+    } else if (key == "host_chunks") {
+        if (value < 0 || value > 16) return fail("host_chunks must be in [0, 16]");
+        ix->host_chunks = value;
     } else if (key == "visited_filter_slots") {
         // -1 = default; 0 = off; otherwise a power of two
         if (value > 0 && (value & (value - 1))) return fail("visited_filter_slots must be a power of two");
@@ -1128,6 +1132,7 @@ int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
     else if (key == "rows_in_flight") *value = ix->rows_in_flight;
     else if (key == "visited_filter_slots") *value = ix->filter_slots;
     else if (key == "generic_kernel") *value = ix->generic_kernel;
+    else if (key == "host_chunks") *value = ix->host_chunks;
     else if (key == "config_search_window_size") *value = ix->cfg_window;
     else if (key == "config_search_buffer_capacity") *value = ix->cfg_capacity;
     else if (key == "config_search_buffer_visited_set") *value = ix->cfg_visited;
@@ -1226,7 +1231,8 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     p.gstride = ix->gstride;
     p.entry_point = ix->entry_point;
     p.entry_points = rep->d_entry;
-    p.n_entry = rep->d_entry ? ix->n_entry : 1;
+    // push_back drops entry points once the buffer is full (search_buffer.h:311-316): only the first `capacity` count
+    p.n_entry = rep->d_entry ? uint32_t(std::min<size_t>(ix->n_entry, capacity)) : 1;
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
     p.lvq = ix->storage == SVSB200_LVQ8;
@@ -1433,9 +1439,20 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
     std::vector<Replica*> used_rep;
     std::vector<size_t> used_lo, used_m;
     int rc = 0;
-    for (size_t r = 0; r < R && rc == 0; ++r) {
+    // Every device's share is cut into C pieces, each on its own stream: the host-to-device copy of piece i+1 and the
+    // device-to-host copy of piece i-1 run under the kernel of piece i (the kernels of consecutive pieces overlap
+    // too -- the next one's CTAs start as the previous one's retire).  C = 1 on a caller's stream (enqueue order is
+    // the caller's) and for small shares.
+    size_t C = 1;
+    if (!stream_ && !ix->counting) {   // (the diagnostic counters describe one launch)
+        const size_t share = (nq + R - 1) / R;
+        C = ix->host_chunks > 0 ? size_t(ix->host_chunks) : (share >= 8192 ? 4 : share >= 2048 ? 2 : 1);
+        C = std::min(C, share);
+    }
+    for (size_t part = 0; part < R * C && rc == 0; ++part) {
+        const size_t r = part / C;
         size_t lo, hi;
-        balance(nq, R, r, &lo, &hi);
+        balance(nq, R * C, part, &lo, &hi);
         if (hi == lo) continue;
         Replica* rep = ix->reps[r].get();
         cudaError_t e = cudaSetDevice(rep->device);
