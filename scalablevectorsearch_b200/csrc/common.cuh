@@ -76,6 +76,7 @@ struct SearchParams {
     uint2* hist;
     uint32_t* hist_count;
     uint32_t hist_cap;
+    uint32_t spec_prefetch;      // lean kernel: 1 = pull the predicted next node's unvisited neighbour rows into L2 one hop ahead
 };
 
 struct LaunchConfig {

@@ -161,6 +161,7 @@ struct svsb200_index {
     // options
     long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
     long generic_kernel = 0;          // 1: force the generic (round-1) kernel instead of the lean one
+    long spec_prefetch = 1;           // lean kernel: L2 prefetch of the predicted next hop's rows
     long host_chunks = 0;             // host-buffer searches: pieces per device whose copies overlap the kernels (0 = auto)
     std::mutex mu;
     Scratch* last = nullptr;          // scratch of the most recent search: counters, kernel time, kernel kind
@@ -1105,6 +1106,9 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
         ix->filter_tag16 = value;
     } else if (key == "generic_kernel") {
         ix->generic_kernel = value;
+    } else if (key == "speculative_prefetch") {
+        if (value < 0 || value > 2) return fail("speculative_prefetch must be 0 (off), 1 (bulk) or 2 (per line)");
+        ix->spec_prefetch = value;
     } else if (key == "host_chunks") {
         if (value < 0 || value > 16) return fail("host_chunks must be in [0, 16]");
         ix->host_chunks = value;
@@ -1133,6 +1137,7 @@ int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
     else if (key == "visited_filter_slots") *value = ix->filter_slots;
     else if (key == "generic_kernel") *value = ix->generic_kernel;
     else if (key == "host_chunks") *value = ix->host_chunks;
+    else if (key == "speculative_prefetch") *value = ix->spec_prefetch;
     else if (key == "config_search_window_size") *value = ix->cfg_window;
     else if (key == "config_search_buffer_capacity") *value = ix->cfg_capacity;
     else if (key == "config_search_buffer_visited_set") *value = ix->cfg_visited;
@@ -1233,6 +1238,8 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     p.entry_points = rep->d_entry;
     // push_back drops entry points once the buffer is full (search_buffer.h:311-316): only the first `capacity` count
     p.n_entry = rep->d_entry ? uint32_t(std::min<size_t>(ix->n_entry, capacity)) : 1;
+    // 1: one bulk prefetch per row (16-byte granules); 2: one line prefetch per 128 bytes of a row
+    p.spec_prefetch = ix->spec_prefetch == 1 ? (ix->row_stride % 16 == 0 ? 1u : 2u) : uint32_t(ix->spec_prefetch);
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
     p.lvq = ix->storage == SVSB200_LVQ8;
