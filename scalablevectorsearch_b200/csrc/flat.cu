@@ -38,7 +38,7 @@ constexpr uint32_t FLAT_A_BYTES = FLAT_BM * FLAT_BK * 2, FLAT_B_BYTES = FLAT_BN 
 constexpr uint32_t FLAT_STAGE_BYTES = FLAT_A_BYTES + FLAT_B_BYTES;
 constexpr uint32_t FLAT_STAGES = 5;
 constexpr uint32_t FLAT_KC = 33;                                     // list entries per (query, base range)
-constexpr uint32_t FLAT_MAX_SPLIT = 15;                              // 15 * 33 <= 512 candidates per query
+constexpr uint32_t FLAT_CMAX = 1024;                                 // candidates per query the rescoring kernel holds
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -130,22 +130,35 @@ struct FlatParams {
     const __half* a_tiles;    // [mtiles][KB] blobs of FLAT_A_BYTES
     const __half* b_tiles;    // [ntiles][KB] blobs of FLAT_B_BYTES
     const float* b_bias;      // [ntiles * FLAT_BN]: |x~|^2 (L2) / 0 (inner product), +inf for padding rows
-    uint32_t KB, ntiles, mtiles, nsplit;
+    uint32_t KB, ntiles, mtiles, nlists;
     float key_scale;          // key = bias + key_scale * s
-    float* cand_key;          // [mtiles * FLAT_BM][nsplit][FLAT_KC]
+    float* cand_key;          // [mtiles * FLAT_BM][nlists][FLAT_KC], pre-filled with (+inf, no id)
     uint32_t* cand_id;
 };
 
-// Shared memory: stages | bias[2][256] | list keys [KC][128] | list ids [KC][128] | barriers | tmem slot
-constexpr size_t kFlatSmem = size_t(FLAT_STAGES) * FLAT_STAGE_BYTES + 2 * FLAT_BN * 4 + 2 * size_t(FLAT_KC) * FLAT_BM * 4 + 256;
+// Work split: the mtiles x ntiles output tiles form one row-major sequence (query tile major), cut into gridDim.x
+// contiguous, equal segments -- every SM gets the same number of tiles whatever the batch size.  A segment may run
+// over a query-tile boundary (the lists are flushed there), and a query tile is covered by a few consecutive CTAs
+// ("pieces"); each piece keeps two lists per query, one per half of the 256 tile columns (one per epilogue warp).
+__host__ __device__ inline uint64_t flat_seg_begin(uint64_t total, uint32_t ctas, uint32_t b) { return total * b / ctas; }
+__host__ __device__ inline uint32_t flat_cta_of_tile(uint64_t t, uint64_t total, uint32_t ctas) {
+    uint32_t b = uint32_t(t * ctas / total);
+    while (b + 1 < ctas && flat_seg_begin(total, ctas, b + 1) <= t) ++b;
+    while (b > 0 && flat_seg_begin(total, ctas, b) > t) --b;
+    return b;
+}
 
-__global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_constant__ FlatParams fp) {
+// Shared memory: stages | bias[2][256] | list keys [2][128][KC] | list ids [2][128][KC] | barriers | tmem slot
+constexpr uint32_t FLAT_EPI_WARPS = 8, FLAT_THREADS = 64 + 32 * FLAT_EPI_WARPS;
+constexpr size_t kFlatSmem = size_t(FLAT_STAGES) * FLAT_STAGE_BYTES + 2 * FLAT_BN * 4 + 2 * 2 * size_t(FLAT_KC) * FLAT_BM * 4 + 256;
+
+__global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const __grid_constant__ FlatParams fp) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* stages = smem;
     float* bias_s = reinterpret_cast<float*>(smem + size_t(FLAT_STAGES) * FLAT_STAGE_BYTES);   // [2][FLAT_BN]
-    uint32_t* lkey = reinterpret_cast<uint32_t*>(bias_s + 2 * FLAT_BN);                         // [128][KC] ordered keys
-    uint32_t* lid = lkey + size_t(FLAT_KC) * FLAT_BM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(lid + size_t(FLAT_KC) * FLAT_BM);
+    uint32_t* lkey = reinterpret_cast<uint32_t*>(bias_s + 2 * FLAT_BN);                         // [2][128][KC] ordered keys
+    uint32_t* lid = lkey + 2 * size_t(FLAT_KC) * FLAT_BM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(lid + 2 * size_t(FLAT_KC) * FLAT_BM);
     uint64_t* full = bars;                       // [STAGES] bytes of a stage have landed
     uint64_t* empty = bars + FLAT_STAGES;        // [STAGES] the MMAs reading a stage have completed
     uint64_t* tmem_full = empty + FLAT_STAGES;   // [2] an accumulator is complete
@@ -154,9 +167,9 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_full + 2);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t mtile = blockIdx.x / fp.nsplit, split = blockIdx.x % fp.nsplit;
-    const uint32_t nt_lo = uint32_t(uint64_t(split) * fp.ntiles / fp.nsplit);
-    const uint32_t nt_hi = uint32_t(uint64_t(split + 1) * fp.ntiles / fp.nsplit);
+    const uint64_t total = uint64_t(fp.mtiles) * fp.ntiles;
+    const uint64_t t_lo = flat_seg_begin(total, gridDim.x, blockIdx.x), t_hi = flat_seg_begin(total, gridDim.x, blockIdx.x + 1);
+    const uint32_t mtile0 = uint32_t(t_lo / fp.ntiles), nt0 = uint32_t(t_lo % fp.ntiles);
 
     if (warp == 0 && lane == 0) {
         for (uint32_t i = 0; i < FLAT_STAGES; ++i) {
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
         }
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(tmem_full + i, 1);
-            mbar_init(tmem_empty + i, 128);
+            mbar_init(tmem_empty + i, 32 * FLAT_EPI_WARPS);
             mbar_init(bias_full + i, 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -182,8 +195,8 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
     if (warp == 0) {
         // ===== producer: one bulk copy per operand blob =====
         if (lane == 0) {
-            uint32_t s = 0, ph = 0;
-            for (uint32_t nt = nt_lo; nt < nt_hi; ++nt) {
+            uint32_t s = 0, ph = 0, mtile = mtile0, nt = nt0;
+            for (uint64_t t = t_lo; t < t_hi; ++t) {
                 for (uint32_t kb = 0; kb < fp.KB; ++kb) {
                     mbar_wait(empty + s, ph ^ 1u);
                     mbar_arrive_expect_tx(full + s, FLAT_STAGE_BYTES);
@@ -198,13 +211,17 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                         ph ^= 1u;
                     }
                 }
+                if (++nt == fp.ntiles) {
+                    nt = 0;
+                    ++mtile;
+                }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: a single thread =====
         if (lane == 0) {
-            uint32_t s = 0, ph = 0, acc = 0, aph = 0;
-            for (uint32_t nt = nt_lo; nt < nt_hi; ++nt) {
+            uint32_t s = 0, ph = 0, acc = 0, aph = 0, nt = nt0;
+            for (uint64_t t = t_lo; t < t_hi; ++t) {
                 mbar_wait(tmem_empty + acc, aph ^ 1u);
                 tc_fence_after();
                 mbar_arrive_expect_tx(bias_full + acc, FLAT_BN * 4);
@@ -230,26 +247,30 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                 tc_commit(tmem_full + acc);
                 acc ^= 1u;
                 if (acc == 0) aph ^= 1u;
+                if (++nt == fp.ntiles) nt = 0;
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32*(w%4) .. +31 = query rows of the tile =====
-        const uint32_t quad = warp & 3u;
+        // ===== epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (= query rows of the tile); the two warps of a
+        // lane quarter take one half of the 256 columns each, with a list of their own per row =====
+        const uint32_t quad = warp & 3u, half = (warp - 2u) >> 2;
         const uint32_t row = quad * 32 + lane;
-        uint32_t acc = 0, aph = 0;
+        uint32_t* my_key = lkey + size_t(half) * FLAT_BM * FLAT_KC;
+        uint32_t* my_id = lid + size_t(half) * FLAT_BM * FLAT_KC;
+        uint32_t acc = 0, aph = 0, mtile = mtile0, nt = nt0;
         float thr = INFINITY;   // this row's threshold: the largest key of its list
         for (uint32_t e = 0; e < FLAT_KC; ++e) {
-            lkey[row * FLAT_KC + e] = flat_ord(INFINITY);
-            lid[row * FLAT_KC + e] = 0xFFFFFFFFu;
+            my_key[row * FLAT_KC + e] = flat_ord(INFINITY);
+            my_id[row * FLAT_KC + e] = 0xFFFFFFFFu;
         }
         __syncwarp();
-        for (uint32_t nt = nt_lo; nt < nt_hi; ++nt) {
+        for (uint64_t t = t_lo; t < t_hi; ++t) {
             mbar_wait(tmem_full + acc, aph);
             mbar_wait(bias_full + acc, aph);
             tc_fence_after();
             const float* bias = bias_s + acc * FLAT_BN;
 #pragma unroll 1
-            for (uint32_t c = 0; c < FLAT_BN / 32; ++c) {
+            for (uint32_t c = half * (FLAT_BN / 64); c < (half + 1) * (FLAT_BN / 64); ++c) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem_base + ((quad * 32u) << 16) + acc * FLAT_BN + c * 32;
                 asm volatile(
@@ -261,9 +282,9 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                       "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                     : "r"(taddr));
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                // keys of the 32 columns; only when the smallest beats the threshold (rare once the list has
-                // settled) are they looked at one by one
-                float key[32];
+                // keys of the 32 columns, in groups of four with the group minimum; only groups whose minimum beats a
+                // row's threshold (rare once the lists have settled) are looked at key by key
+                float key[32], gmin[8];
                 float best = INFINITY;
 #pragma unroll
                 for (uint32_t i4 = 0; i4 < 8; ++i4) {
@@ -272,21 +293,26 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
                     key[4 * i4 + 1] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 1]), b4.y);
                     key[4 * i4 + 2] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 2]), b4.z);
                     key[4 * i4 + 3] = fmaf(fp.key_scale, __uint_as_float(v[4 * i4 + 3]), b4.w);
-                    best = fminf(fminf(fminf(best, key[4 * i4 + 0]), fminf(key[4 * i4 + 1], key[4 * i4 + 2])), key[4 * i4 + 3]);
+                    gmin[i4] = fminf(fminf(key[4 * i4 + 0], key[4 * i4 + 1]), fminf(key[4 * i4 + 2], key[4 * i4 + 3]));
+                    best = fminf(best, gmin[i4]);
                 }
-                // (warp-uniform branch; inside, one key at a time: the lanes whose key beats their row's threshold are
-                // served in turn by the whole warp)
+                // (warp-uniform branches; inside, one key at a time: the lanes whose key beats their row's threshold
+                // are served in turn by the whole warp)
                 if (__any_sync(0xFFFFFFFFu, best < thr)) {
 #pragma unroll
-                    for (uint32_t i = 0; i < 32; ++i) {
-                        uint32_t hits = __ballot_sync(0xFFFFFFFFu, key[i] < thr);
-                        while (hits) {
-                            const uint32_t src = uint32_t(__ffs(int(hits)) - 1);
-                            hits &= hits - 1;
-                            const float k_src = __shfl_sync(0xFFFFFFFFu, key[i], src);
-                            const float t = flat_list_replace_max(lkey, lid, quad * 32 + src, lane, k_src,
-                                                                  nt * FLAT_BN + c * 32 + i);
-                            if (lane == src) thr = t;
+                    for (uint32_t i4 = 0; i4 < 8; ++i4) {
+                        if (!__any_sync(0xFFFFFFFFu, gmin[i4] < thr)) continue;
+#pragma unroll
+                        for (uint32_t i = 4 * i4; i < 4 * i4 + 4; ++i) {
+                            uint32_t hits = __ballot_sync(0xFFFFFFFFu, key[i] < thr);
+                            while (hits) {
+                                const uint32_t src = uint32_t(__ffs(int(hits)) - 1);
+                                hits &= hits - 1;
+                                const float k_src = __shfl_sync(0xFFFFFFFFu, key[i], src);
+                                const float tnew = flat_list_replace_max(my_key, my_id, quad * 32 + src, lane, k_src,
+                                                                         nt * FLAT_BN + c * 32 + i);
+                                if (lane == src) thr = tnew;
+                            }
                         }
                     }
                 }
@@ -295,15 +321,24 @@ __global__ void __launch_bounds__(192, 1) flat_gemm_topk_kernel(const __grid_con
             mbar_arrive(tmem_empty + acc);
             acc ^= 1u;
             if (acc == 0) aph ^= 1u;
-        }
-        // lists out: unfilled entries are (+inf, no id)
-        const size_t q = size_t(mtile) * FLAT_BM + row;
-        float* ok = fp.cand_key + (q * fp.nsplit + split) * FLAT_KC;
-        uint32_t* oi = fp.cand_id + (q * fp.nsplit + split) * FLAT_KC;
-        __syncwarp();
-        for (uint32_t e = 0; e < FLAT_KC; ++e) {
-            ok[e] = flat_unord(lkey[row * FLAT_KC + e]);
-            oi[e] = lid[row * FLAT_KC + e];
+            if (++nt == fp.ntiles || t + 1 == t_hi) {
+                // the query tile (or this CTA's part of it) is finished: lists out, lists reset
+                const uint32_t piece = blockIdx.x - flat_cta_of_tile(uint64_t(mtile) * fp.ntiles, total, gridDim.x);
+                const size_t q = size_t(mtile) * FLAT_BM + row;
+                float* ok = fp.cand_key + (q * fp.nlists + piece * 2 + half) * FLAT_KC;
+                uint32_t* oi = fp.cand_id + (q * fp.nlists + piece * 2 + half) * FLAT_KC;
+                __syncwarp();
+                for (uint32_t e = 0; e < FLAT_KC; ++e) {
+                    ok[e] = flat_unord(my_key[row * FLAT_KC + e]);
+                    oi[e] = my_id[row * FLAT_KC + e];
+                    my_key[row * FLAT_KC + e] = flat_ord(INFINITY);
+                    my_id[row * FLAT_KC + e] = 0xFFFFFFFFu;
+                }
+                __syncwarp();
+                thr = INFINITY;
+                nt = 0;
+                ++mtile;
+            }
         }
     }
     tc_fence_before();
@@ -375,7 +410,7 @@ __global__ void __launch_bounds__(32, 16) flat_rescore_kernel(const __grid_const
     constexpr int G = 16 / Row<ROWT>::LPT;
     constexpr int GROUPS = 32 / G;
     constexpr unsigned FULL = 0xFFFFFFFFu;
-    constexpr uint32_t CMAX = 512;
+    constexpr uint32_t CMAX = FLAT_CMAX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float* q_s = reinterpret_cast<float*>(smem_raw);
     uint32_t* cid = reinterpret_cast<uint32_t*>(q_s + p.qstride);   // [CMAX]
@@ -473,8 +508,33 @@ cudaError_t flat_tile_rows(int srct, const void* src, uint32_t row_stride, uint3
     return cudaGetLastError();
 }
 
+__global__ void flat_fill_kernel(float* __restrict__ key, uint32_t* __restrict__ id, size_t count) {
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < count; i += size_t(gridDim.x) * blockDim.x) {
+        key[i] = INFINITY;
+        id[i] = 0xFFFFFFFFu;
+    }
+}
+
+// Grid size and lists per query for a problem: as many CTAs as SMs, fewer while a query tile would be cut into more
+// pieces than the rescoring kernel holds candidates for (small batches over a large base).
+void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ctas, uint32_t* nlists) {
+    const uint64_t total = uint64_t(mtiles) * ntiles;
+    uint32_t g = uint32_t(std::min<uint64_t>(sm_count, total));
+    for (;; --g) {
+        uint32_t pieces = 1;
+        for (uint32_t m = 0; m < mtiles; ++m)
+            pieces = std::max(pieces, flat_cta_of_tile(uint64_t(m + 1) * ntiles - 1, total, g) -
+                                          flat_cta_of_tile(uint64_t(m) * ntiles, total, g) + 1);
+        if (2 * pieces * FLAT_KC <= FLAT_CMAX || g == 1) {
+            *ctas = g;
+            *nlists = 2 * pieces;
+            return;
+        }
+    }
+}
+
 cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float* b_bias, uint32_t KB, uint32_t ntiles,
-                           uint32_t mtiles, uint32_t nsplit, float key_scale, float* cand_key, uint32_t* cand_id,
+                           uint32_t mtiles, uint32_t ctas, uint32_t nlists, float key_scale, float* cand_key, uint32_t* cand_id,
                            cudaStream_t stream) {
     FlatParams fp{};
     fp.a_tiles = static_cast<const __half*>(a_tiles);
@@ -483,19 +543,22 @@ cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float
     fp.KB = KB;
     fp.ntiles = ntiles;
     fp.mtiles = mtiles;
-    fp.nsplit = nsplit;
+    fp.nlists = nlists;
     fp.key_scale = key_scale;
     fp.cand_key = cand_key;
     fp.cand_id = cand_id;
     cudaError_t err = cudaFuncSetAttribute(flat_gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(kFlatSmem));
     if (err != cudaSuccess) return err;
-    flat_gemm_topk_kernel<<<mtiles * nsplit, 192, kFlatSmem, stream>>>(fp);
+    const size_t entries = size_t(mtiles) * FLAT_BM * nlists * FLAT_KC;
+    flat_fill_kernel<<<unsigned(std::min<size_t>(4096, (entries + 255) / 256)), 256, 0, stream>>>(cand_key, cand_id, entries);
+    count_launch();
+    flat_gemm_topk_kernel<<<ctas, FLAT_THREADS, kFlatSmem, stream>>>(fp);
     count_launch();
     return cudaGetLastError();
 }
 
 template <int ROWT> static cudaError_t rescore_rowt(int op, const SearchParams& p, const RescoreParams& rp, cudaStream_t stream) {
-    const size_t smem = size_t(p.qstride) * 4 + 512 * 4 * 3;
+    const size_t smem = size_t(p.qstride) * 4 + size_t(FLAT_CMAX) * 4 * 3;
     if (op == OP_L2F) flat_rescore_kernel<ROWT, OP_L2F><<<rp.nq, 32, smem, stream>>>(p, rp);
     else if (op == OP_IPF) flat_rescore_kernel<ROWT, OP_IPF><<<rp.nq, 32, smem, stream>>>(p, rp);
     else return cudaErrorInvalidValue;

@@ -222,37 +222,6 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             }
             __syncwarp();
 
-            // ---- one hop ahead: rows of the predicted next node's neighbours into L2 ----
-            // nxt[] (requested at the top of this hop) has landed behind this hop's rows.  A read-only probe of the
-            // visited filter -- final for this hop -- picks the neighbours the next hop will evaluate; one bulk
-            // prefetch per row then runs under the merge, so the next hop's row loads find their lines in L2.
-            // Nothing here changes state: a wrong prediction (3% of hops) only costs the traffic.
-            if (p.spec_prefetch && staged_node != NONE) {
-#pragma unroll
-                for (int w = 0; w < kFastMaxGW; ++w) {
-                    if (w * 32u < p.gstride) {
-                        const uint32_t id = nxt[w];
-                        if (id != kNoNeighbor) {
-                            const uint32_t tag2 = (id >> p.filter_shift) * 0x00010001u;
-                            const uint4 set = filt[id & fmask];
-                            const uint32_t x0 = set.x ^ tag2, x1 = set.y ^ tag2, x2 = set.z ^ tag2, x3 = set.w ^ tag2;
-                            const uint32_t hit = (((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) |
-                                                  ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3)) & 0x80008000u;
-                            if (hit == 0u) {
-                                const char* row = vectors + size_t(id) * p.row_stride;
-                                if (p.spec_prefetch == 1) {
-                                    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(row), "r"(p.row_stride) : "memory");
-                                } else {
-#pragma unroll 1
-                                    for (uint32_t off = 0; off < p.row_stride; off += 128)
-                                        asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off) : "memory");
-                                }
-                            }
-                        }
-                    }
-                }
-            }
-
             // ---- merge, 32 candidates at a time (each group == its sequential inserts) ----
 #pragma unroll 1
             for (uint32_t r0 = 0; r0 < ncand; r0 += 32) {

@@ -161,7 +161,6 @@ struct svsb200_index {
     // options
     long warps_per_cta = 0, ctas_per_sm = 0, rows_in_flight = 0, filter_slots = -1, filter_tag16 = 1, no_split = 0;
     long generic_kernel = 0;          // 1: force the generic (round-1) kernel instead of the lean one
-    long spec_prefetch = 1;           // lean kernel: L2 prefetch of the predicted next hop's rows
     long host_chunks = 0;             // host-buffer searches: pieces per device whose copies overlap the kernels (0 = auto)
     std::mutex mu;
     Scratch* last = nullptr;          // scratch of the most recent search: counters, kernel time, kernel kind
@@ -1106,9 +1105,6 @@ int svsb200_set_option(svsb200_index* ix, const char* name, long value) {
         ix->filter_tag16 = value;
     } else if (key == "generic_kernel") {
         ix->generic_kernel = value;
-    } else if (key == "speculative_prefetch") {
-        if (value < 0 || value > 2) return fail("speculative_prefetch must be 0 (off), 1 (bulk) or 2 (per line)");
-        ix->spec_prefetch = value;
     } else if (key == "host_chunks") {
         if (value < 0 || value > 16) return fail("host_chunks must be in [0, 16]");
         ix->host_chunks = value;
@@ -1137,7 +1133,6 @@ int svsb200_get_option(svsb200_index* ix, const char* name, long* value) {
     else if (key == "visited_filter_slots") *value = ix->filter_slots;
     else if (key == "generic_kernel") *value = ix->generic_kernel;
     else if (key == "host_chunks") *value = ix->host_chunks;
-    else if (key == "speculative_prefetch") *value = ix->spec_prefetch;
     else if (key == "config_search_window_size") *value = ix->cfg_window;
     else if (key == "config_search_buffer_capacity") *value = ix->cfg_capacity;
     else if (key == "config_search_buffer_visited_set") *value = ix->cfg_visited;
@@ -1238,8 +1233,6 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     p.entry_points = rep->d_entry;
     // push_back drops entry points once the buffer is full (search_buffer.h:311-316): only the first `capacity` count
     p.n_entry = rep->d_entry ? uint32_t(std::min<size_t>(ix->n_entry, capacity)) : 1;
-    // 1: one bulk prefetch per row (16-byte granules); 2: one line prefetch per 128 bytes of a row
-    p.spec_prefetch = ix->spec_prefetch == 1 ? (ix->row_stride % 16 == 0 ? 1u : 2u) : uint32_t(ix->spec_prefetch);
     p.greater = metric != SVSB200_L2;
     p.sq = ix->storage == SVSB200_SQ;
     p.lvq = ix->storage == SVSB200_LVQ8;
@@ -1453,7 +1446,7 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
     size_t C = 1;
     if (!stream_ && !ix->counting) {   // (the diagnostic counters describe one launch)
         const size_t share = (nq + R - 1) / R;
-        C = ix->host_chunks > 0 ? size_t(ix->host_chunks) : (share >= 8192 ? 4 : share >= 2048 ? 2 : 1);
+        C = ix->host_chunks > 0 ? size_t(ix->host_chunks) : (share >= 8192 ? 8 : share >= 2048 ? 4 : share >= 512 ? 2 : 1);
         C = std::min(C, share);
     }
     for (size_t part = 0; part < R * C && rc == 0; ++part) {
@@ -1882,26 +1875,9 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
             CUDA_TRY(cudaStreamSynchronize(stream));
         }
     }
-    // Base ranges per query tile, from a cost model of the kernel (measured, profiles/flat_r2.json): a CTA's tile
-    // takes max(MMA time, epilogue time); the epilogue pays ~150 instructions per list update, and a query sees
-    // KC ln(rows_in_range / KC) updates per range -- so more ranges mean more updates, fewer ranges fewer CTAs
-    // (one CTA per SM: the grid runs in waves of sm_count).
-    uint32_t nsplit = 1;
-    {
-        const double kc = double(flat_kc()), sms = double(rep->sm_count);
-        double best = 1e300;
-        for (uint32_t c = 1; c <= std::min(15u, ntiles); ++c) {
-            const double rows = double(n) / c, tiles_per_cta = double(ntiles) / c;
-            const double updates_per_warp_tile = 32.0 * kc * std::max(1.0, std::log(rows / kc)) / tiles_per_cta;
-            const double tile_cycles = std::max(270.0 * KB, 3.0 * (600.0 + 150.0 * updates_per_warp_tile));
-            const double waves = std::ceil(double(mtiles) * c / sms);
-            const double cost = waves * tiles_per_cta * tile_cycles;
-            if (cost < best) {
-                best = cost;
-                nsplit = c;
-            }
-        }
-    }
+    // one CTA per SM over equal runs of output tiles; `nsplit` = candidate lists per query (flat.cu: flat_plan)
+    uint32_t flat_ctas = 1, nsplit = 2;
+    flat_plan(mtiles, ntiles, uint32_t(rep->sm_count), &flat_ctas, &nsplit);
     const size_t qrow = size_t(dim) * esize(qdtype);
     CUDA_TRY(sc->flat_a.ensure(size_t(mtiles) * 128 * KB * 32 * 2));
     CUDA_TRY(sc->flat_qnorm.ensure(size_t(mtiles) * 128));
@@ -1910,7 +1886,7 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
     CUDA_TRY(sc->flat_unv.ensure(nq + 1));
     CUDA_TRY(flat_tile_rows(qdtype, d_queries, uint32_t(qrow), uint32_t(nq), dim, 128, 1.0f, 0, sc->flat_a.ptr, nullptr,
                             sc->flat_qnorm.ptr, nullptr, stream));
-    CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, nsplit, l2 ? -2.0f : -1.0f,
+    CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, flat_ctas, nsplit, l2 ? -2.0f : -1.0f,
                             sc->flat_ckey.ptr, sc->flat_cid.ptr, stream));
     // exact re-scoring with the search path's distance code: prepared queries as for a search
     const uint32_t qstride = uint32_t(round_up(ix->dim, 16));

@@ -434,19 +434,21 @@ def test_cancellation_predicate(dataset, ref_outputs):
     # a long batch (large window, many queries): cancel after the first poll, compare with the uncancelled time
     index.search_parameters.buffer_config = SearchBufferConfig(400, 400)
     q = np.tile(dataset.queries, (300, 1))
-    t0 = time.perf_counter()
+    index.search(q, 10)   # (first call of this size: scratch allocation)
     index.search(q, 10)
-    full = time.perf_counter() - t0
+    full_ms = index.last_kernel_ms()
     calls = []
 
     def fire():
         calls.append(1)
         return len(calls) > 2
-    t0 = time.perf_counter()
     index.search(q, 10, cancel=fire)
-    cancelled = time.perf_counter() - t0
+    cancelled_ms = index.last_kernel_ms()
     assert len(calls) > 2
-    assert cancelled < 0.7 * full, (cancelled, full)
+    # the kernels stop at the next hop / query boundary: the search kernel of the batch's last piece (host batches are
+    # cut into pieces whose copies overlap the kernels) runs a fraction of its uncancelled time.  Wall time is no
+    # measure here: the pageable copies of 300k queries dominate it.
+    assert cancelled_ms < 0.5 * full_ms, (cancelled_ms, full_ms)
 
 
 def test_sharded_index_in_one_process_matches_reference_per_shard_plus_merge(dataset, oracle):
