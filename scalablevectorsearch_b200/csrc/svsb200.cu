@@ -1219,7 +1219,7 @@ static int search_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const 
     }
     CUDA_TRY(err);
     CUDA_TRY(cudaMemsetAsync(sc->d_counter, 0, sizeof(unsigned int), stream));
-    CUDA_TRY(cudaMemsetAsync(sc->d_cancel, 0, sizeof(int), stream));
+    // (sc->d_cancel is zero here: only wait_kernels raises it, and lowers it again once the kernels have finished)
 
     SearchParams p{};
     p.vectors = rep->d_vectors;
@@ -1394,6 +1394,7 @@ int svsb200_search_device(svsb200_index* ix, const void* d_queries, int qdtype, 
 static int wait_kernels(const std::vector<Scratch*>& scs, int (*cancel)(void*), void* cancel_arg) {
     if (!cancel) return 0;   // nothing to poll for: the stream order of the copies behind the kernels is enough
     bool raised = false;
+    int rc = 0;
     for (;;) {
         bool busy = false;
         for (Scratch* sc : scs) {
@@ -1401,18 +1402,28 @@ static int wait_kernels(const std::vector<Scratch*>& scs, int (*cancel)(void*), 
             cudaSetDevice(sc->device);
             cudaError_t q = cudaEventQuery(sc->ev_stop);
             if (q == cudaErrorNotReady) busy = true;
-            else if (q != cudaSuccess) return fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+            else if (q != cudaSuccess) rc = fail(std::string("cudaEventQuery: ") + cudaGetErrorString(q));
         }
-        if (!busy) return 0;
+        if (!busy || rc) break;
         if (!raised && cancel(cancel_arg)) {
+            raised = true;
             for (Scratch* sc : scs) {
                 cudaSetDevice(sc->device);
-                CUDA_TRY(cudaMemsetAsync(sc->d_cancel, 1, sizeof(int), sc->ctl));
+                cudaError_t e = cudaMemsetAsync(sc->d_cancel, 1, sizeof(int), sc->ctl);
+                if (e != cudaSuccess) rc = fail(std::string("cudaMemsetAsync: ") + cudaGetErrorString(e));
             }
-            raised = true;
         }
         std::this_thread::sleep_for(std::chrono::microseconds(20));
     }
+    if (raised) {   // the kernels are done (or failed): lower the flags for the next search of these scratch sets
+        for (Scratch* sc : scs) {
+            cudaSetDevice(sc->device);
+            cudaStreamSynchronize(sc->stream);
+            cudaMemsetAsync(sc->d_cancel, 0, sizeof(int), sc->ctl);
+            cudaStreamSynchronize(sc->ctl);
+        }
+    }
+    return rc;
 }
 static int wait_all(const std::vector<Scratch*>& scs) {
     for (Scratch* sc : scs) {
@@ -1444,7 +1455,7 @@ int svsb200_search_cancellable(svsb200_index* ix, const void* queries, int qdtyp
     // too -- the next one's CTAs start as the previous one's retire).  C = 1 on a caller's stream (enqueue order is
     // the caller's) and for small shares.
     size_t C = 1;
-    if (!stream_ && !ix->counting) {   // (the diagnostic counters describe one launch)
+    if (!stream_ && !ix->counting && !cancel) {   // (the diagnostic counters describe one launch; a predicate: one piece)
         const size_t share = (nq + R - 1) / R;
         C = ix->host_chunks > 0 ? size_t(ix->host_chunks) : (share >= 8192 ? 8 : share >= 2048 ? 4 : share >= 512 ? 2 : 1);
         C = std::min(C, share);

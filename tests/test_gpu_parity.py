@@ -445,9 +445,9 @@ def test_cancellation_predicate(dataset, ref_outputs):
     index.search(q, 10, cancel=fire)
     cancelled_ms = index.last_kernel_ms()
     assert len(calls) > 2
-    # the kernels stop at the next hop / query boundary: the search kernel of the batch's last piece (host batches are
-    # cut into pieces whose copies overlap the kernels) runs a fraction of its uncancelled time.  Wall time is no
-    # measure here: the pageable copies of 300k queries dominate it.
+    # the kernel stops at the next hop / query boundary and runs a fraction of the uncancelled time (`full_ms`: the
+    # last piece of the batch, which spans the whole run -- without a predicate a host batch is cut into pieces whose
+    # copies overlap the kernels).  Wall time is no measure here: the pageable copies of 300k queries dominate it.
     assert cancelled_ms < 0.5 * full_ms, (cancelled_ms, full_ms)
 
 
