@@ -131,15 +131,20 @@ struct FlatParams {
     const __half* b_tiles;    // [ntiles][KB] blobs of FLAT_B_BYTES
     const float* b_bias;      // [ntiles * FLAT_BN]: |x~|^2 (L2) / 0 (inner product), +inf for padding rows
     uint32_t KB, ntiles, mtiles, nlists;
+    uint32_t share;           // R: CTAs that walk the same base tiles at the same time, on R consecutive query tiles
     float key_scale;          // key = bias + key_scale * s
     float* cand_key;          // [mtiles * FLAT_BM][nlists][FLAT_KC], pre-filled with (+inf, no id)
     uint32_t* cand_id;
 };
 
-// Work split: the mtiles x ntiles output tiles form one row-major sequence (query tile major), cut into gridDim.x
-// contiguous, equal segments -- every SM gets the same number of tiles whatever the batch size.  A segment may run
-// over a query-tile boundary (the lists are flushed there), and a query tile is covered by a few consecutive CTAs
-// ("pieces"); each piece keeps two lists per query, one per half of the 256 tile columns (one per epilogue warp).
+// Work split: query tiles are taken R at a time ("row groups"); the (row group, base tile) pairs form one row-major
+// sequence, cut into G = gridDim.x / R contiguous, equal segments -- every SM gets the same number of tiles whatever
+// the batch size.  Segment g is walked by R CTAs (blockIdx g, g + G, ...: all resident at once, started together, doing
+// identical work), one per query tile of the row group: they ask for the same base tile within microseconds of each
+// other, so all but the first request are served by L2 -- without this, 148 CTAs stream 148 different places of a
+// base that is many times the L2 and every operand byte comes from DRAM (measured: 97 GB for 1M x 768).  A segment
+// may run over a row-group boundary (the lists are flushed there), and a query tile is covered by a few consecutive
+// segments ("pieces"); each piece keeps two lists per query, one per half of the 256 tile columns (one per epilogue warp).
 __host__ __device__ inline uint64_t flat_seg_begin(uint64_t total, uint32_t ctas, uint32_t b) { return total * b / ctas; }
 __host__ __device__ inline uint32_t flat_cta_of_tile(uint64_t t, uint64_t total, uint32_t ctas) {
     uint32_t b = uint32_t(t * ctas / total);
@@ -167,9 +172,13 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_full + 2);
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t total = uint64_t(fp.mtiles) * fp.ntiles;
-    const uint64_t t_lo = flat_seg_begin(total, gridDim.x, blockIdx.x), t_hi = flat_seg_begin(total, gridDim.x, blockIdx.x + 1);
-    const uint32_t mtile0 = uint32_t(t_lo / fp.ntiles), nt0 = uint32_t(t_lo % fp.ntiles);
+    const uint32_t nseg = gridDim.x / fp.share, seg = blockIdx.x % nseg, member = blockIdx.x / nseg;
+    const uint32_t ngroups = (fp.mtiles + fp.share - 1) / fp.share;
+    const uint64_t total = uint64_t(ngroups) * fp.ntiles;
+    const uint64_t t_lo = flat_seg_begin(total, nseg, seg), t_hi = flat_seg_begin(total, nseg, seg + 1);
+    // (a CTA's query tile advances by `share` at a row-group boundary; tiles of a query tile past the last one are skipped
+    // by every role alike)
+    const uint32_t mtile0 = uint32_t(t_lo / fp.ntiles) * fp.share + member, nt0 = uint32_t(t_lo % fp.ntiles);
 
     if (warp == 0 && lane == 0) {
         for (uint32_t i = 0; i < FLAT_STAGES; ++i) {
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
         if (lane == 0) {
             uint32_t s = 0, ph = 0, mtile = mtile0, nt = nt0;
             for (uint64_t t = t_lo; t < t_hi; ++t) {
-                for (uint32_t kb = 0; kb < fp.KB; ++kb) {
+                for (uint32_t kb = 0; kb < fp.KB && mtile < fp.mtiles; ++kb) {
                     mbar_wait(empty + s, ph ^ 1u);
                     mbar_arrive_expect_tx(full + s, FLAT_STAGE_BYTES);
                     uint8_t* st = stages + size_t(s) * FLAT_STAGE_BYTES;
@@ -213,15 +222,22 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
                 }
                 if (++nt == fp.ntiles) {
                     nt = 0;
-                    ++mtile;
+                    mtile += fp.share;
                 }
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer: a single thread =====
         if (lane == 0) {
-            uint32_t s = 0, ph = 0, acc = 0, aph = 0, nt = nt0;
+            uint32_t s = 0, ph = 0, acc = 0, aph = 0, nt = nt0, mtile = mtile0;
             for (uint64_t t = t_lo; t < t_hi; ++t) {
+                if (mtile >= fp.mtiles) {
+                    if (++nt == fp.ntiles) {
+                        nt = 0;
+                        mtile += fp.share;
+                    }
+                    continue;
+                }
                 mbar_wait(tmem_empty + acc, aph ^ 1u);
                 tc_fence_after();
                 mbar_arrive_expect_tx(bias_full + acc, FLAT_BN * 4);
@@ -247,7 +263,10 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
                 tc_commit(tmem_full + acc);
                 acc ^= 1u;
                 if (acc == 0) aph ^= 1u;
-                if (++nt == fp.ntiles) nt = 0;
+                if (++nt == fp.ntiles) {
+                    nt = 0;
+                    mtile += fp.share;
+                }
             }
         }
     } else {
@@ -265,6 +284,13 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
         }
         __syncwarp();
         for (uint64_t t = t_lo; t < t_hi; ++t) {
+            if (mtile >= fp.mtiles) {
+                if (++nt == fp.ntiles) {
+                    nt = 0;
+                    mtile += fp.share;
+                }
+                continue;
+            }
             mbar_wait(tmem_full + acc, aph);
             mbar_wait(bias_full + acc, aph);
             tc_fence_after();
@@ -323,7 +349,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
             if (acc == 0) aph ^= 1u;
             if (++nt == fp.ntiles || t + 1 == t_hi) {
                 // the query tile (or this CTA's part of it) is finished: lists out, lists reset
-                const uint32_t piece = blockIdx.x - flat_cta_of_tile(uint64_t(mtile) * fp.ntiles, total, gridDim.x);
+                const uint32_t piece = seg - flat_cta_of_tile(uint64_t(mtile / fp.share) * fp.ntiles, total, nseg);
                 const size_t q = size_t(mtile) * FLAT_BM + row;
                 float* ok = fp.cand_key + (q * fp.nlists + piece * 2 + half) * FLAT_KC;
                 uint32_t* oi = fp.cand_id + (q * fp.nlists + piece * 2 + half) * FLAT_KC;
@@ -337,7 +363,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
                 __syncwarp();
                 thr = INFINITY;
                 nt = 0;
-                ++mtile;
+                mtile += fp.share;
             }
         }
     }
@@ -515,18 +541,22 @@ __global__ void flat_fill_kernel(float* __restrict__ key, uint32_t* __restrict__
     }
 }
 
-// Grid size and lists per query for a problem: as many CTAs as SMs, fewer while a query tile would be cut into more
-// pieces than the rescoring kernel holds candidates for (small batches over a large base).
-void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ctas, uint32_t* nlists) {
-    const uint64_t total = uint64_t(mtiles) * ntiles;
-    uint32_t g = uint32_t(std::min<uint64_t>(sm_count, total));
+// Grid size, sharing factor and lists per query for a problem: as many CTAs as SMs in groups of R, fewer segments
+// while a query tile would be cut into more pieces than the rescoring kernel holds candidates for (small batches
+// over a large base).
+void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ctas, uint32_t* share, uint32_t* nlists) {
+    const uint32_t R = mtiles >= 8 ? 4 : mtiles >= 4 ? 2 : 1;
+    const uint32_t ngroups = (mtiles + R - 1) / R;
+    const uint64_t total = uint64_t(ngroups) * ntiles;
+    uint32_t g = uint32_t(std::min<uint64_t>(std::max(1u, sm_count / R), total));
     for (;; --g) {
         uint32_t pieces = 1;
-        for (uint32_t m = 0; m < mtiles; ++m)
+        for (uint32_t m = 0; m < ngroups; ++m)
             pieces = std::max(pieces, flat_cta_of_tile(uint64_t(m + 1) * ntiles - 1, total, g) -
                                           flat_cta_of_tile(uint64_t(m) * ntiles, total, g) + 1);
         if (2 * pieces * FLAT_KC <= FLAT_CMAX || g == 1) {
-            *ctas = g;
+            *ctas = g * R;
+            *share = R;
             *nlists = 2 * pieces;
             return;
         }
@@ -534,8 +564,8 @@ void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ct
 }
 
 cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float* b_bias, uint32_t KB, uint32_t ntiles,
-                           uint32_t mtiles, uint32_t ctas, uint32_t nlists, float key_scale, float* cand_key, uint32_t* cand_id,
-                           cudaStream_t stream) {
+                           uint32_t mtiles, uint32_t ctas, uint32_t share, uint32_t nlists, float key_scale, float* cand_key,
+                           uint32_t* cand_id, cudaStream_t stream) {
     FlatParams fp{};
     fp.a_tiles = static_cast<const __half*>(a_tiles);
     fp.b_tiles = static_cast<const __half*>(b_tiles);
@@ -544,6 +574,7 @@ cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float
     fp.ntiles = ntiles;
     fp.mtiles = mtiles;
     fp.nlists = nlists;
+    fp.share = share;
     fp.key_scale = key_scale;
     fp.cand_key = cand_key;
     fp.cand_id = cand_id;

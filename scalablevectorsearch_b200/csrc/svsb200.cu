@@ -1887,8 +1887,8 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
         }
     }
     // one CTA per SM over equal runs of output tiles; `nsplit` = candidate lists per query (flat.cu: flat_plan)
-    uint32_t flat_ctas = 1, nsplit = 2;
-    flat_plan(mtiles, ntiles, uint32_t(rep->sm_count), &flat_ctas, &nsplit);
+    uint32_t flat_ctas = 1, flat_share = 1, nsplit = 2;
+    flat_plan(mtiles, ntiles, uint32_t(rep->sm_count), &flat_ctas, &flat_share, &nsplit);
     const size_t qrow = size_t(dim) * esize(qdtype);
     CUDA_TRY(sc->flat_a.ensure(size_t(mtiles) * 128 * KB * 32 * 2));
     CUDA_TRY(sc->flat_qnorm.ensure(size_t(mtiles) * 128));
@@ -1897,7 +1897,7 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
     CUDA_TRY(sc->flat_unv.ensure(nq + 1));
     CUDA_TRY(flat_tile_rows(qdtype, d_queries, uint32_t(qrow), uint32_t(nq), dim, 128, 1.0f, 0, sc->flat_a.ptr, nullptr,
                             sc->flat_qnorm.ptr, nullptr, stream));
-    CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, flat_ctas, nsplit, l2 ? -2.0f : -1.0f,
+    CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, flat_ctas, flat_share, nsplit, l2 ? -2.0f : -1.0f,
                             sc->flat_ckey.ptr, sc->flat_cid.ptr, stream));
     // exact re-scoring with the search path's distance code: prepared queries as for a search
     const uint32_t qstride = uint32_t(round_up(ix->dim, 16));
