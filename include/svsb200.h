@@ -167,7 +167,10 @@ uint64_t svsb200_launch_count(void);
 /* Tuning knobs (performance only; results never change):
  *   "warps_per_cta", "ctas_per_sm", "rows_in_flight" (0 restores the default);
  *   "visited_filter_slots": size of the per-query exact visited filter, the GPU form of
- *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n >= 8). */
+ *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n >= 8);
+ *   "host_chunks": pieces a host-buffer batch is cut into per device so that the copies of one piece run under
+ *   the kernel of another (0 = automatic: up to 8 for large batches; one piece when a cancel predicate or a
+ *   caller stream is given). */
 int svsb200_set_option(svsb200_index* index, const char* name, long value);
 /* Reads a knob back; also "last_kernel": which kernel the most recent search ran on (1 = the lean
  * one-warp-per-CTA kernel, 0 = the generic kernel that covers every other configuration), and

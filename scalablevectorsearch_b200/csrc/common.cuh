@@ -117,7 +117,7 @@ cudaError_t flat_tile_rows(int srct, const void* src, uint32_t row_stride, uint3
                            cudaStream_t stream);
 cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float* b_bias, uint32_t KB, uint32_t ntiles,
                            uint32_t mtiles, uint32_t ctas, uint32_t share, uint32_t nlists, float key_scale, float* cand_key,
-                           uint32_t* cand_id, cudaStream_t stream);
+                           uint32_t* cand_id, uint32_t* progress, cudaStream_t stream);
 struct SearchParams;
 void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ctas, uint32_t* share, uint32_t* nlists);
 cudaError_t flat_rescore(int rowt, int op, const SearchParams& p, const float* cand_key, const uint32_t* cand_id, uint32_t nsplit,

@@ -38,6 +38,7 @@ constexpr uint32_t FLAT_A_BYTES = FLAT_BM * FLAT_BK * 2, FLAT_B_BYTES = FLAT_BN 
 constexpr uint32_t FLAT_STAGE_BYTES = FLAT_A_BYTES + FLAT_B_BYTES;
 constexpr uint32_t FLAT_STAGES = 5;
 constexpr uint32_t FLAT_KC = 33;                                     // list entries per (query, base range)
+constexpr uint32_t FLAT_LEAD = 2;                                    // tiles a CTA may run ahead of its segment's slowest CTA
 constexpr uint32_t FLAT_CMAX = 1024;                                 // candidates per query the rescoring kernel holds
 
 // ---- PTX helpers -------------------------------------------------------------------------------------------
@@ -132,6 +133,7 @@ struct FlatParams {
     const float* b_bias;      // [ntiles * FLAT_BN]: |x~|^2 (L2) / 0 (inner product), +inf for padding rows
     uint32_t KB, ntiles, mtiles, nlists;
     uint32_t share;           // R: CTAs that walk the same base tiles at the same time, on R consecutive query tiles
+    uint32_t* progress;       // [gridDim.x] tiles started by each CTA (zeroed before the launch)
     float key_scale;          // key = bias + key_scale * s
     float* cand_key;          // [mtiles * FLAT_BM][nlists][FLAT_KC], pre-filled with (+inf, no id)
     uint32_t* cand_id;
@@ -205,7 +207,27 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
         // ===== producer: one bulk copy per operand blob =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0, mtile = mtile0, nt = nt0;
+            bool in_step = fp.share > 1;
             for (uint64_t t = t_lo; t < t_hi; ++t) {
+                // Keep the CTAs of a segment within FLAT_LEAD tiles of each other: identical work drifts apart by the
+                // data-dependent list updates, and a base tile only stays in L2 for some tens of microseconds while
+                // 37 segments stream through it.  The CTA that is ahead waits (bounded: all CTAs of the grid are
+                // resident -- one per SM -- but nothing is assumed; after a timeout this CTA stops looking).
+                if (in_step) {
+                    const uint32_t mine = uint32_t(t - t_lo) + 1u;
+                    volatile uint32_t* prog = fp.progress;
+                    prog[blockIdx.x] = mine;
+                    for (uint32_t spin = 0;; ++spin) {
+                        uint32_t slowest = mine;
+                        for (uint32_t m = 0; m < fp.share; ++m) slowest = min(slowest, prog[seg + m * nseg]);
+                        if (slowest + FLAT_LEAD >= mine) break;
+                        if (spin > (1u << 16)) {
+                            in_step = false;
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
+                }
                 for (uint32_t kb = 0; kb < fp.KB && mtile < fp.mtiles; ++kb) {
                     mbar_wait(empty + s, ph ^ 1u);
                     mbar_arrive_expect_tx(full + s, FLAT_STAGE_BYTES);
@@ -565,7 +587,7 @@ void flat_plan(uint32_t mtiles, uint32_t ntiles, uint32_t sm_count, uint32_t* ct
 
 cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float* b_bias, uint32_t KB, uint32_t ntiles,
                            uint32_t mtiles, uint32_t ctas, uint32_t share, uint32_t nlists, float key_scale, float* cand_key,
-                           uint32_t* cand_id, cudaStream_t stream) {
+                           uint32_t* cand_id, uint32_t* progress, cudaStream_t stream) {
     FlatParams fp{};
     fp.a_tiles = static_cast<const __half*>(a_tiles);
     fp.b_tiles = static_cast<const __half*>(b_tiles);
@@ -575,6 +597,7 @@ cudaError_t flat_gemm_topk(const void* a_tiles, const void* b_tiles, const float
     fp.mtiles = mtiles;
     fp.nlists = nlists;
     fp.share = share;
+    fp.progress = progress;
     fp.key_scale = key_scale;
     fp.cand_key = cand_key;
     fp.cand_id = cand_id;

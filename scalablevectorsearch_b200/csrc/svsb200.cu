@@ -83,6 +83,7 @@ struct Scratch {
     DeviceBuffer<unsigned char> flat_a, flat_q2;       // tensor-core flat search: query tiles, gathered queries
     DeviceBuffer<float> flat_qnorm, flat_ckey, flat_d2;
     DeviceBuffer<uint32_t> flat_cid, flat_unv;         // candidates, unverified list (+ its counter in slot 0)
+    DeviceBuffer<uint32_t> flat_progress;              // per CTA of the flat GEMM: tiles started (keeps row groups in step)
     DeviceBuffer<uint64_t> flat_i2;
     DeviceBuffer<uint64_t> gather_ids, merged_ids;     // sharded search (on the merging device)
     DeviceBuffer<float> gather_dists, merged_dists;
@@ -100,7 +101,7 @@ struct Scratch {
         gather_ids.release(); merged_ids.release(); gather_dists.release(); merged_dists.release();
         exh_ids.release(); exh_dists.release();
         flat_a.release(); flat_q2.release(); flat_qnorm.release(); flat_ckey.release(); flat_d2.release();
-        flat_cid.release(); flat_unv.release(); flat_i2.release();
+        flat_cid.release(); flat_unv.release(); flat_i2.release(); flat_progress.release();
         if (d_counter) cudaFree(d_counter);
         if (d_cancel) cudaFree(d_cancel);
         if (ev_start) cudaEventDestroy(ev_start);
@@ -1895,10 +1896,12 @@ static int flat_on_device(svsb200_index* ix, Replica* rep, Scratch* sc, const vo
     CUDA_TRY(sc->flat_ckey.ensure(size_t(mtiles) * 128 * nsplit * flat_kc()));
     CUDA_TRY(sc->flat_cid.ensure(size_t(mtiles) * 128 * nsplit * flat_kc()));
     CUDA_TRY(sc->flat_unv.ensure(nq + 1));
+    CUDA_TRY(sc->flat_progress.ensure(flat_ctas));
+    CUDA_TRY(cudaMemsetAsync(sc->flat_progress.ptr, 0, size_t(flat_ctas) * 4, stream));
     CUDA_TRY(flat_tile_rows(qdtype, d_queries, uint32_t(qrow), uint32_t(nq), dim, 128, 1.0f, 0, sc->flat_a.ptr, nullptr,
                             sc->flat_qnorm.ptr, nullptr, stream));
     CUDA_TRY(flat_gemm_topk(sc->flat_a.ptr, rep->flat_b, rep->flat_bias, KB, ntiles, mtiles, flat_ctas, flat_share, nsplit, l2 ? -2.0f : -1.0f,
-                            sc->flat_ckey.ptr, sc->flat_cid.ptr, stream));
+                            sc->flat_ckey.ptr, sc->flat_cid.ptr, sc->flat_progress.ptr, stream));
     // exact re-scoring with the search path's distance code: prepared queries as for a search
     const uint32_t qstride = uint32_t(round_up(ix->dim, 16));
     CUDA_TRY(sc->q_f32.ensure(nq * qstride));
