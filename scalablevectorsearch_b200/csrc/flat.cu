@@ -36,7 +36,7 @@ namespace svsb200 {
 constexpr uint32_t FLAT_BM = 128, FLAT_BN = 256, FLAT_BK = 32;      // tile sizes (rows, rows, k elements per blob)
 constexpr uint32_t FLAT_A_BYTES = FLAT_BM * FLAT_BK * 2, FLAT_B_BYTES = FLAT_BN * FLAT_BK * 2;
 constexpr uint32_t FLAT_STAGE_BYTES = FLAT_A_BYTES + FLAT_B_BYTES;
-constexpr uint32_t FLAT_STAGES = 5;
+constexpr uint32_t FLAT_STAGES = 6;
 constexpr uint32_t FLAT_KC = 33;                                     // list entries per (query, base range)
 constexpr uint32_t FLAT_LEAD = 4;                                    // tiles a CTA may run ahead of its segment's slowest CTA
 constexpr uint32_t FLAT_CMAX = 1024;                                 // candidates per query the rescoring kernel holds
@@ -156,7 +156,7 @@ __host__ __device__ inline uint32_t flat_cta_of_tile(uint64_t t, uint64_t total,
 }
 
 // Shared memory: stages | bias[2][256] | list keys [2][128][KC] | list ids [2][128][KC] | barriers | tmem slot
-constexpr uint32_t FLAT_EPI_WARPS = 8, FLAT_THREADS = 64 + 32 * FLAT_EPI_WARPS + 32;   // + the pacing warp
+constexpr uint32_t FLAT_EPI_WARPS = 8, FLAT_THREADS = 64 + 32 * FLAT_EPI_WARPS;
 constexpr size_t kFlatSmem = size_t(FLAT_STAGES) * FLAT_STAGE_BYTES + 2 * FLAT_BN * 4 + 2 * 2 * size_t(FLAT_KC) * FLAT_BM * 4 + 256;
 
 __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const __grid_constant__ FlatParams fp) {
@@ -172,8 +172,6 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
     uint64_t* tmem_empty = tmem_full + 2;        // [2] the epilogue has drained an accumulator
     uint64_t* bias_full = tmem_empty + 2;        // [2] the bias tile of an accumulator has landed
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_full + 2);
-    volatile uint32_t* pace_cur = tmem_slot + 2;     // tiles this CTA's producer has started
-    volatile uint32_t* pace_limit = tmem_slot + 3;   // tiles it may start: the segment's slowest CTA + FLAT_LEAD
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t nseg = gridDim.x / fp.share, seg = blockIdx.x % nseg, member = blockIdx.x / nseg;
@@ -194,8 +192,6 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
             mbar_init(tmem_empty + i, 32 * FLAT_EPI_WARPS);
             mbar_init(bias_full + i, 1);
         }
-        *pace_cur = 0;
-        *pace_limit = FLAT_LEAD;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // one warp allocates all 512 TMEM columns (two 256-column accumulators)
@@ -211,15 +207,28 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
         // ===== producer: one bulk copy per operand blob =====
         if (lane == 0) {
             uint32_t s = 0, ph = 0, mtile = mtile0, nt = nt0;
-            bool in_step = fp.share > 1;
+            // Pacing: the R CTAs of a segment do identical work but drift apart by their data-dependent list updates, and a
+            // base tile only stays in L2 for some tens of microseconds while the other segments stream through it.  Every
+            // other tile the producer publishes its progress and, if it is more than FLAT_LEAD tiles ahead of the
+            // segment's slowest CTA, waits (bounded: all CTAs of the grid are resident -- one per SM -- but nothing is
+            // assumed; after a timeout this CTA stops looking).  Only for wide rows: with few k-blocks per tile the
+            // operands are not DRAM-bound and the L2 round trips of the exchange would cost more than they save.
+            bool in_step = fp.share > 1 && fp.KB >= 8;
             for (uint64_t t = t_lo; t < t_hi; ++t) {
-                // Pacing (see the pacing warp below): do not run more than FLAT_LEAD tiles ahead of the segment's
-                // slowest CTA.  Bounded: after a timeout this CTA stops looking.
-                if (fp.share > 1) {
+                if (in_step && ((t - t_lo) & 1u) == 0) {
                     const uint32_t mine = uint32_t(t - t_lo) + 1u;
-                    *pace_cur = mine;
-                    for (uint32_t spin = 0; in_step && mine > *pace_limit; ++spin)
-                        if (spin > (1u << 22)) in_step = false;
+                    volatile uint32_t* prog = fp.progress;
+                    prog[blockIdx.x] = mine;
+                    for (uint32_t spin = 0;; ++spin) {
+                        uint32_t slowest = mine;
+                        for (uint32_t m = 0; m < fp.share; ++m) slowest = min(slowest, prog[seg + m * nseg]);
+                        if (slowest + FLAT_LEAD >= mine) break;
+                        if (spin > (1u << 16)) {
+                            in_step = false;
+                            break;
+                        }
+                        __nanosleep(200);
+                    }
                 }
                 for (uint32_t kb = 0; kb < fp.KB && mtile < fp.mtiles; ++kb) {
                     mbar_wait(empty + s, ph ^ 1u);
@@ -240,7 +249,7 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
                     mtile += fp.share;
                 }
             }
-            *pace_cur = 0xFFFFFFFFu;   // finished: never the slowest again
+            if (fp.share > 1) fp.progress[blockIdx.x] = 0xFFFFFFFFu;   // finished: never the slowest again
         }
     } else if (warp == 1) {
         // ===== MMA issuer: a single thread =====
@@ -283,23 +292,6 @@ __global__ void __launch_bounds__(FLAT_THREADS, 1) flat_gemm_topk_kernel(const _
                     nt = 0;
                     mtile += fp.share;
                 }
-            }
-        }
-    } else if (warp == 2 + FLAT_EPI_WARPS) {
-        // ===== pacing: the R CTAs of a segment do identical work but drift apart by their data-dependent list updates,
-        // and a base tile only stays in L2 for some tens of microseconds while the other segments stream through it.
-        // One thread publishes this CTA's progress and reads the others' (L2 round trips, off the producer's path);
-        // the producer only compares two shared-memory words. =====
-        if (lane == 0 && fp.share > 1) {
-            volatile uint32_t* prog = fp.progress;
-            for (;;) {
-                const uint32_t mine = *pace_cur;
-                prog[blockIdx.x] = mine;
-                uint32_t slowest = 0xFFFFFFFFu;
-                for (uint32_t m = 0; m < fp.share; ++m) slowest = min(slowest, prog[seg + m * nseg]);
-                *pace_limit = slowest > 0xFFFFFFFFu - FLAT_LEAD ? 0xFFFFFFFFu : slowest + FLAT_LEAD;
-                if (mine == 0xFFFFFFFFu) break;
-                __nanosleep(500);
             }
         }
     } else {
