@@ -39,6 +39,14 @@ template <int ROWT, int OP, int DS, int KS> constexpr int fast_min_blocks() {
 #endif
 }
 
+#ifdef SVSB200_PHASE_CLOCKS
+// Diagnostic build only (scratch/build_variant.sh): SM cycles per phase of a hop, summed over all queries by lane 0.
+static __device__ unsigned long long g_phase_clocks[8];   // (one copy per translation unit; fast_f32.cu exports its own)
+#define PHASE_CLOCK(var) const long long var = clock64()
+#else
+#define PHASE_CLOCK(var)
+#endif
+
 // HIST = true is the graph builder's form (build.cu): every expanded node is appended, with its key, to the
 // query's search history -- the reference's `use_full_search_history` candidate pool (vamana_build.h:344-352).
 template <int ROWT, int OP, int DS, int KS, bool HIST = false>
@@ -110,6 +118,10 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             // cancellation inside a search (greedy_search.h:155): polled here, consumed at the end of the hop
             const int cancelled = p.cancel ? *reinterpret_cast<const volatile int*>(p.cancel) : 0;
             uint32_t ncand = 0;
+            PHASE_CLOCK(pc0);
+#ifdef SVSB200_PHASE_CLOCKS
+            long long pc1 = pc0, pc2 = pc0;
+#endif
             if (first) {
                 first = 0;
                 if (uint32_t(lane) < E) cid[lane] = E > 1 ? p.entry_points[lane] : p.entry_point;
@@ -165,6 +177,9 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 n_hist += (n_hist < p.hist_cap) ? 1u : 0u;
             }
             cursor = pos + 1;
+#ifdef SVSB200_PHASE_CLOCKS
+            pc1 = clock64();
+#endif
 
             // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
             // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember.  Races between
@@ -201,6 +216,9 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 n_fetched += ncand;
             }
             __syncwarp();
+#ifdef SVSB200_PHASE_CLOCKS
+            pc2 = clock64();
+#endif
             }   // !first
             if (ncand == 0) {
                 if (cancelled) break;
@@ -221,6 +239,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 }
             }
             __syncwarp();
+            PHASE_CLOCK(pc3);
 
             // ---- merge, 32 candidates at a time (each group == its sequential inserts) ----
 #pragma unroll 1
@@ -323,6 +342,16 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 cursor = min(cursor, minpos);   // best_unvisited = min(best_unvisited, i) (:401)
                 __syncwarp();
             }
+#ifdef SVSB200_PHASE_CLOCKS
+            if (lane == 0) {
+                const long long pc4 = clock64();
+                atomicAdd(&g_phase_clocks[0], (unsigned long long)(pc1 - pc0));
+                atomicAdd(&g_phase_clocks[1], (unsigned long long)(pc2 - pc1));
+                atomicAdd(&g_phase_clocks[2], (unsigned long long)(pc3 - pc2));
+                atomicAdd(&g_phase_clocks[3], (unsigned long long)(pc4 - pc3));
+                atomicAdd(&g_phase_clocks[4], 1ull);
+            }
+#endif
             if (cancelled) break;
         }
 
