@@ -16,9 +16,7 @@ k = 10
 out = {}
 st = torch.cuda.current_stream().cuda_stream or 1
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-for mode in (0, 1, 2):
-  index.set_option("speculative_prefetch", mode)
-  for nq in (10000, 5000, 2500, 1250, 148, 32):
+for nq in (10000, 5000, 2500, 1250, 625, 148, 32):
     ids = torch.empty((nq, k), dtype=torch.int64, device="cuda"); d = torch.empty((nq, k), dtype=torch.float32, device="cuda")
     ts = []
     for it in range(8):
@@ -26,5 +24,5 @@ for mode in (0, 1, 2):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(); index.search_device(dq.data_ptr(), queries.dtype, nq, k, ids.data_ptr(), d.data_ptr(), stream=st); e.record()
         torch.cuda.synchronize(); ts.append(s.elapsed_time(e))
-    out[f"prefetch{mode}_nq{nq}"] = round(float(np.median(ts[3:])), 4)
+    out[nq] = round(float(np.median(ts[3:])), 4)
 print(json.dumps({"workload": name, "ms_by_batch": out, "note": "L2 flushed between launches; events around the whole enqueue (prepare + search kernels)"}))
