@@ -145,10 +145,16 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                             filt[slot] = make_uint4((set.x << 16) | tag, __funnelshift_l(set.x, set.y, 16),
                                                     __funnelshift_l(set.y, set.z, 16), __funnelshift_l(set.z, set.w, 16));
                             if constexpr (SPEC) {
+                                // (a prefetch moves one 32-byte sector, not the 128-byte line: measured -- with one
+                                // prefetch per line the next hop's loads still waited for DRAM)
                                 const char* row = vectors + size_t(ids[w]) * p.row_stride;
+                                const char* end = row + p.row_stride;
 #pragma unroll 1
-                                for (uint32_t off = 0; off < p.row_stride; off += 128)
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off) : "memory");
+                                for (; row < end; row += 128)
+                                    asm volatile(
+                                        "prefetch.global.L2 [%0];\n\tprefetch.global.L2 [%0+32];\n\t"
+                                        "prefetch.global.L2 [%0+64];\n\tprefetch.global.L2 [%0+96];" ::"l"(row)
+                                        : "memory");
                             }
                         }
                     }
@@ -312,6 +318,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 }
             }
             __syncwarp();
+            PHASE_CLOCK(pc2b);
 
             // ---- the predicted next hop's filter pass, one hop early (filter_row, SPEC): it runs here, behind this hop's
             // row loads (nxt[] has landed with them), so that the rows it asks for travel to L2 under the merge ----
@@ -424,7 +431,8 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 const long long pc4 = clock64();
                 atomicAdd(&g_phase_clocks[0], (unsigned long long)(pc1 - pc0));
                 atomicAdd(&g_phase_clocks[1], (unsigned long long)(pc2 - pc1));
-                atomicAdd(&g_phase_clocks[2], (unsigned long long)(pc3 - pc2));
+                atomicAdd(&g_phase_clocks[2], (unsigned long long)(pc2b - pc2));
+                atomicAdd(&g_phase_clocks[5], (unsigned long long)(pc3 - pc2b));
                 atomicAdd(&g_phase_clocks[3], (unsigned long long)(pc4 - pc3));
                 atomicAdd(&g_phase_clocks[4], 1ull);
             }
