@@ -145,16 +145,16 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                             filt[slot] = make_uint4((set.x << 16) | tag, __funnelshift_l(set.x, set.y, 16),
                                                     __funnelshift_l(set.y, set.z, 16), __funnelshift_l(set.z, set.w, 16));
                             if constexpr (SPEC) {
-                                // (a prefetch moves one 32-byte sector, not the 128-byte line: measured -- with one
-                                // prefetch per line the next hop's loads still waited for DRAM)
+                                // An asynchronous 4-byte copy per 128-byte line into a scratch word of shared memory, with
+                                // the L2::128B prefetch size: unlike `prefetch.global.L2` (measured: no effect here --
+                                // prefetches that miss the TLB are dropped, and random rows mostly do) it is a real load,
+                                // so the line is translated, fetched and left in L2; no register waits for it.
                                 const char* row = vectors + size_t(ids[w]) * p.row_stride;
-                                const char* end = row + p.row_stride;
+                                const uint32_t dummy = uint32_t(__cvta_generic_to_shared(spec_ins + kFastMaxGW + lane));
 #pragma unroll 1
-                                for (; row < end; row += 128)
-                                    asm volatile(
-                                        "prefetch.global.L2 [%0];\n\tprefetch.global.L2 [%0+32];\n\t"
-                                        "prefetch.global.L2 [%0+64];\n\tprefetch.global.L2 [%0+96];" ::"l"(row)
-                                        : "memory");
+                                for (uint32_t off = 0; off < p.row_stride; off += 128)
+                                    asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 4;" ::"r"(dummy), "l"(row + off)
+                                                 : "memory");
                             }
                         }
                     }
