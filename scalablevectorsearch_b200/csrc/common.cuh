@@ -98,8 +98,8 @@ __host__ __device__ inline size_t warp_smem_bytes(uint32_t qstride, uint32_t cap
 // Per-CTA (= per-warp = per-query) shared memory of the fast kernel, mirrored on the host.
 __host__ __device__ inline size_t fast_smem_bytes(uint32_t qstride, uint32_t cap_pad, uint32_t deg_pad,
                                                   uint32_t filter_bytes) {
-    // filter | query | buffer {key,id} | candidate keys | candidate ids | next hop's candidate ids | its insert masks | 32 scratch words (async-copy targets)
-    return size_t((filter_bytes + 15u) & ~15u) + size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 12 + 16 + 128;
+    // filter | query | buffer {key,id} | candidate keys | candidate ids
+    return size_t((filter_bytes + 15u) & ~15u) + size_t(qstride) * 4 + size_t(cap_pad) * 8 + size_t(deg_pad) * 8;
 }
 
 constexpr int kFastMaxGW = 4;   // adjacency rows up to 128 neighbours (4 x 32) are register-staged

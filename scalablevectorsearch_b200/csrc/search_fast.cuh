@@ -25,8 +25,6 @@
 
 #include "search_kernel.cuh"
 
-#include <type_traits>
-
 namespace svsb200 {
 
 // Resident CTAs (= warps = queries) per SM the compiler must allow for: 24 (80 registers) where the
@@ -74,8 +72,6 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
     uint2* buf = reinterpret_cast<uint2*>(q_s + p.qstride);                  // [cap_pad] {key bits, id | visited}
     float* ckey = reinterpret_cast<float*>(buf + p.cap_pad);                 // [deg_pad] candidate keys
     uint32_t* cid = reinterpret_cast<uint32_t*>(ckey + p.deg_pad);           // [deg_pad] candidate ids
-    uint32_t* scid = cid + p.deg_pad;                                        // [deg_pad] candidates of the predicted next hop
-    uint32_t* spec_ins = scid + p.deg_pad;                                   // [kFastMaxGW] lanes whose tag the speculative pass pushed
 
     const float ksign = p.greater ? -1.0f : 1.0f;   // keys = sign * distance, ordered by '<'
     const uint32_t C = p.capacity, W = p.window;
@@ -111,63 +107,11 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
         uint32_t size = 0, cursor = 0, n_hops = 0, n_evals = E, n_fetched = E;
         uint32_t n_hist = 0;
         uint32_t staged_node = NONE;          // node whose adjacency row sits in nxt[]
-        uint32_t spec_ncand = NONE;           // != NONE: scid[] holds staged_node's neighbours that passed the filter
         uint32_t nxt[kFastMaxGW];
 #pragma unroll
         for (int w = 0; w < kFastMaxGW; ++w) nxt[w] = kNoNeighbor;
         int first = 1;
         asm volatile("" : "+r"(first));   // opaque: keeps the compiler from peeling (= duplicating) the first hop
-
-        // emplace_visited over one adjacency row (search_buffer.h:462-464): ids that pass are compacted (adjacency
-        // order kept) into out[]; a hit -> skip, else remember.  Races between lanes on one set can only lose an
-        // update (a later false "fresh"), never invent a hit.  SPEC: this is the predicted next hop's row -- the lanes
-        // that pushed a tag are recorded (so that a wrong prediction can take the tags back out) and every fresh row
-        // is pulled into L2, where the next hop's loads will find it.
-        auto filter_row = [&](const uint32_t (&ids)[kFastMaxGW], uint32_t* out, auto spec_tag) -> uint32_t {
-            constexpr bool SPEC = decltype(spec_tag)::value;
-            uint32_t count = 0;
-#pragma unroll
-            for (int w = 0; w < kFastMaxGW; ++w) {
-                if (w * 32u < p.gstride) {
-                    bool fresh = ids[w] != kNoNeighbor;
-                    if (fresh) {   // the filter is always on here (the host routes filter-off runs to the generic kernel)
-                        const uint32_t slot = ids[w] & fmask;
-                        const uint32_t tag = ids[w] >> p.filter_shift;
-                        const uint32_t tag2 = tag * 0x00010001u;
-                        const uint4 set = filt[slot];
-                        // any 16-bit half of the set equal to the tag?  x ^ tag2 has a zero half exactly then;
-                        // (v - 0x00010001) & ~v & 0x80008000 is non-zero iff v has a zero half.
-                        const uint32_t x0 = set.x ^ tag2, x1 = set.y ^ tag2, x2 = set.z ^ tag2, x3 = set.w ^ tag2;
-                        const uint32_t hit = (((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) |
-                                              ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3)) & 0x80008000u;
-                        fresh = hit == 0u;
-                        if (fresh) {   // push the new tag in front, drop the oldest
-                            filt[slot] = make_uint4((set.x << 16) | tag, __funnelshift_l(set.x, set.y, 16),
-                                                    __funnelshift_l(set.y, set.z, 16), __funnelshift_l(set.z, set.w, 16));
-                            if constexpr (SPEC) {
-                                // An asynchronous 4-byte copy per 128-byte line into a scratch word of shared memory, with
-                                // the L2::128B prefetch size: unlike `prefetch.global.L2` (measured: no effect here --
-                                // prefetches that miss the TLB are dropped, and random rows mostly do) it is a real load,
-                                // so the line is translated, fetched and left in L2; no register waits for it.
-                                const char* row = vectors + size_t(ids[w]) * p.row_stride;
-                                const uint32_t dummy = uint32_t(__cvta_generic_to_shared(spec_ins + kFastMaxGW + lane));
-#pragma unroll 1
-                                for (uint32_t off = 0; off < p.row_stride; off += 128)
-                                    asm volatile("cp.async.ca.shared.global.L2::128B [%0], [%1], 4;" ::"r"(dummy), "l"(row + off)
-                                                 : "memory");
-                            }
-                        }
-                    }
-                    const unsigned m = __ballot_sync(FULL, fresh);
-                    if constexpr (SPEC) {
-                        if (lane == 0) spec_ins[w] = m;
-                    }
-                    if (fresh) out[count + __popc(m & lt_mask)] = ids[w];
-                    count += __popc(m);
-                }
-            }
-            return count;
-        };
 
         // ---- main loop: while (!buffer.done()) (greedy_search.h:153) ----
         for (;;) {
@@ -210,48 +154,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             // loads into the same registers.  nb[] is copied out BEFORE the next prefetch is issued into nxt[]:
             // the write-after-read dependence keeps the prefetch loads behind every wait on this hop's row, so
             // their latency is never waited for here (they have a whole hop to land).
-            const bool predicted = node == staged_node;
-            if (!predicted) {
-                // The speculative pass of the previous hop pushed tags for a node that is not expanded now: take them
-                // back out (the halves equal to the tag become the empty marker; the tag that was dropped from the far
-                // end stays forgotten, which can only cause a re-evaluation later -- never a wrong skip).  nxt[] still
-                // holds that node's row.
-                if (spec_ncand != NONE) {
-                    // One word at a time; a lane only writes when it finds its tag, and the word is repeated until no lane
-                    // finds one: two lanes of a word can share a set, and a removal overwritten by the other lane's
-                    // read-modify-write must not be lost -- a tag left behind would hide a node that was never evaluated.
-#pragma unroll
-                    for (int w = 0; w < kFastMaxGW; ++w) {
-                        if (w * 32u < p.gstride) {
-                            const bool mine = (spec_ins[w] >> lane) & 1u;
-                            const uint32_t slot = nxt[w] & fmask;
-                            const uint32_t tag2 = (nxt[w] >> p.filter_shift) * 0x00010001u;
-#pragma unroll 1
-                            for (;;) {
-                                bool found_tag = false;
-                                if (mine) {
-                                    uint4 set = filt[slot];
-                                    // exact per-half zero test: 0x8000 in every 16-bit half of x that is zero
-                                    auto zero_halves = [](uint32_t x) {
-                                        return ~(((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x | 0x7FFF7FFFu);
-                                    };
-                                    const uint32_t z0 = zero_halves(set.x ^ tag2), z1 = zero_halves(set.y ^ tag2);
-                                    const uint32_t z2 = zero_halves(set.z ^ tag2), z3 = zero_halves(set.w ^ tag2);
-                                    found_tag = (z0 | z1 | z2 | z3) != 0u;
-                                    if (found_tag) {
-                                        set.x |= (z0 >> 15) * 0xFFFFu;
-                                        set.y |= (z1 >> 15) * 0xFFFFu;
-                                        set.z |= (z2 >> 15) * 0xFFFFu;
-                                        set.w |= (z3 >> 15) * 0xFFFFu;
-                                        filt[slot] = set;
-                                    }
-                                }
-                                __syncwarp();
-                                if (!__any_sync(FULL, found_tag)) break;
-                            }
-                        }
-                    }
-                }
+            if (node != staged_node) {
                 const uint32_t* grow = p.graph + size_t(node) * p.gstride;
 #pragma unroll
                 for (int w = 0; w < kFastMaxGW; ++w)
@@ -260,8 +163,6 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             uint32_t nb[kFastMaxGW];
 #pragma unroll
             for (int w = 0; w < kFastMaxGW; ++w) nb[w] = nxt[w];
-            const uint32_t ready = predicted ? spec_ncand : NONE;   // this hop's filter pass has already run
-            spec_ncand = NONE;
             staged_node = NONE;
             if (pred_pos != NONE) {
                 staged_node = buf[pred_pos].y & kIdMask;
@@ -280,12 +181,32 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
             pc1 = clock64();
 #endif
 
-            if (ready != NONE) {
-                // the candidates were compacted one hop ago (their rows are on their way into L2)
-                ncand = ready;
-                for (uint32_t i = lane; i < ncand; i += 32) cid[i] = scid[i];
-            } else {
-                ncand = filter_row(nb, cid, std::false_type{});
+            // Ids that pass the visited filter are compacted (adjacency order kept) into cid[].
+            // emplace_visited (search_buffer.h:462-464): hit -> skip, else remember.  Races between
+            // lanes on one set can only lose an update (a later false "fresh"), never invent a hit.
+#pragma unroll
+            for (int w = 0; w < kFastMaxGW; ++w) {
+                if (w * 32u < p.gstride) {
+                    bool fresh = nb[w] != kNoNeighbor;
+                    if (fresh) {   // the filter is always on here (the host routes filter-off runs to the generic kernel)
+                        const uint32_t slot = nb[w] & fmask;
+                        const uint32_t tag = nb[w] >> p.filter_shift;
+                        const uint32_t tag2 = tag * 0x00010001u;
+                        const uint4 set = filt[slot];
+                        // any 16-bit half of the set equal to the tag?  x ^ tag2 has a zero half exactly then;
+                        // (v - 0x00010001) & ~v & 0x80008000 is non-zero iff v has a zero half.
+                        const uint32_t x0 = set.x ^ tag2, x1 = set.y ^ tag2, x2 = set.z ^ tag2, x3 = set.w ^ tag2;
+                        const uint32_t hit = (((x0 - 0x00010001u) & ~x0) | ((x1 - 0x00010001u) & ~x1) |
+                                              ((x2 - 0x00010001u) & ~x2) | ((x3 - 0x00010001u) & ~x3)) & 0x80008000u;
+                        fresh = hit == 0u;
+                        if (fresh)   // push the new tag in front, drop the oldest
+                            filt[slot] = make_uint4((set.x << 16) | tag, __funnelshift_l(set.x, set.y, 16),
+                                                    __funnelshift_l(set.y, set.z, 16), __funnelshift_l(set.z, set.w, 16));
+                    }
+                    const unsigned m = __ballot_sync(FULL, fresh);
+                    if (fresh) cid[ncand + __popc(m & lt_mask)] = nb[w];
+                    ncand += __popc(m);
+                }
             }
             if (p.hops) {
                 ++n_hops;
@@ -318,11 +239,6 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 }
             }
             __syncwarp();
-            PHASE_CLOCK(pc2b);
-
-            // ---- the predicted next hop's filter pass, one hop early (filter_row, SPEC): it runs here, behind this hop's
-            // row loads (nxt[] has landed with them), so that the rows it asks for travel to L2 under the merge ----
-            if (staged_node != NONE) spec_ncand = filter_row(nxt, scid, std::true_type{});
             PHASE_CLOCK(pc3);
 
             // ---- merge, 32 candidates at a time (each group == its sequential inserts) ----
@@ -431,8 +347,7 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 const long long pc4 = clock64();
                 atomicAdd(&g_phase_clocks[0], (unsigned long long)(pc1 - pc0));
                 atomicAdd(&g_phase_clocks[1], (unsigned long long)(pc2 - pc1));
-                atomicAdd(&g_phase_clocks[2], (unsigned long long)(pc2b - pc2));
-                atomicAdd(&g_phase_clocks[5], (unsigned long long)(pc3 - pc2b));
+                atomicAdd(&g_phase_clocks[2], (unsigned long long)(pc3 - pc2));
                 atomicAdd(&g_phase_clocks[3], (unsigned long long)(pc4 - pc3));
                 atomicAdd(&g_phase_clocks[4], 1ull);
             }

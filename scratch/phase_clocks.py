@@ -24,5 +24,5 @@ for cold in (0, 1):
         lib.svsb200_debug_phase_clocks(buf, 1)
     v = list(buf); hops = max(1, v[4])
     out[f"{'cold' if cold else 'warm'}_{nq}"] = {"kernel_ms": round(index.last_kernel_ms(), 4), "hops": v[4], "cycles_per_hop": {"next+adjacency": round(v[0] / hops), "filter": round(v[1] / hops),
-               "distances": round(v[2] / hops), "next_hop_filter": round(v[5] / hops), "merge": round(v[3] / hops)}}
+               "distances": round(v[2] / hops), "merge": round(v[3] / hops)}}
 print(json.dumps(out))
