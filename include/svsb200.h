@@ -169,7 +169,7 @@ uint64_t svsb200_launch_count(void);
  *   "visited_filter_slots": size of the per-query exact visited filter, the GPU form of
  *   VamanaSearchParameters::search_buffer_visited_set_ (-1 default, 0 off, else 2^n >= 8);
  *   "host_chunks": pieces a host-buffer batch is cut into per device so that the copies of one piece run under
- *   the kernel of another (0 = automatic: up to 8 for large batches; one piece when a cancel predicate or a
+ *   the kernel of another (0 = automatic: up to 4 for large batches; one piece when a cancel predicate or a
  *   caller stream is given). */
 int svsb200_set_option(svsb200_index* index, const char* name, long value);
 /* Reads a knob back; also "last_kernel": which kernel the most recent search ran on (1 = the lean
