@@ -55,3 +55,21 @@ def test_flat_on_the_reference_dataset_with_ties_and_odd_shapes(dataset):
         for q, k in ((dataset.queries[:130], 25), (dataset.queries[:7].astype(np.float16), 1)):
             (ei, ed, _), (fi, fd, _) = _both(index, q, k)
             assert np.array_equal(fi, ei) and np.array_equal(bits(fd), bits(ed)), (metric, k)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("n,nq,dim", [(40_000, 1100, 96), (30_000, 600, 256), (20_000, 1300, 272)])
+def test_flat_row_groups_and_pacing(n, nq, dim):
+    """Batches of >= 4 query tiles are walked in row groups (2 or 4 CTAs on the same base tiles, csrc/flat.cu): 9 tiles =
+    two full groups and one with three absent tiles; 5 tiles = pairs with one absent; rows of >= 256 elements switch
+    the producers' pacing on; 272 is not a multiple of the 32-element k-block."""
+    from scalablevectorsearch_b200 import DistanceType, Vamana
+    from scalablevectorsearch_b200.synthetic import clustered_unit_vectors
+    base, queries = clustered_unit_vectors(n, nq, dim)
+    graph = np.zeros((n, 2), dtype=np.uint32)
+    for metric in (DistanceType.L2, DistanceType.MIP):
+        index = Vamana.from_arrays(base, graph, 0, metric)
+        (ei, ed, _), (fi, fd, nfb) = _both(index, queries, 10)
+        assert np.array_equal(fi, ei), (metric, n, nq, dim)
+        assert np.array_equal(bits(fd), bits(ed))
+        assert nfb < nq // 2
