@@ -149,7 +149,9 @@ __global__ void __launch_bounds__(32, fast_min_blocks<ROWT, OP, DS, KS>()) vaman
                 pos += 32;
             }
             if (!found) break;   // done()
-            const uint32_t node = buf[pos].y;
+            // (masked: lane 0 sets the visited bit of this entry below, and nothing orders that store behind the other
+            // lanes' read of it -- compute-sanitizer racecheck, round 2)
+            const uint32_t node = buf[pos].y & kIdMask;
             // graph.get_node(node): staged in registers by the previous hop if the prediction held; a miss
             // loads into the same registers.  nb[] is copied out BEFORE the next prefetch is issued into nxt[]:
             // the write-after-read dependence keeps the prefetch loads behind every wait on this hop's row, so

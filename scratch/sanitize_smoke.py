@@ -38,6 +38,8 @@ ix.search_parameters.buffer_config = SearchBufferConfig(40, 50); ix.search(q, 10
 allowed = np.zeros(n, dtype=np.uint8); allowed[::3] = 1
 ix.search_filtered(q[:64], 5, allowed)
 ix.range_search(q[:16], 150.0)
+if os.environ.get("SANITIZE_LIGHT"):
+    print("round-2 sanitize workload done (light: no flat search / builder)"); sys.exit(0)
 ix.flat_search(q, 10)                        # 3 query tiles: one CTA per segment
 ix.flat_search(np.tile(q, (3, 1)), 10)       # 8 query tiles: row groups of 4
 ix16 = Vamana.from_arrays(x.astype(np.float16), g, 1, DistanceType.MIP); ix16.flat_search(q[:130].astype(np.float16), 25)
