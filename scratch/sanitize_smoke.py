@@ -9,6 +9,12 @@ def graph(n, R):
     for i in range(n):
         d = rng.integers(1, R + 1); nb = rng.choice(n, size=d, replace=False); g[i, 0] = d; g[i, 1:1 + d] = nb
     return g
+if os.environ.get("SANITIZE_LIGHT") == "2":   # one float32 index, the lean kernel only (racecheck analysis)
+    x = rng.standard_normal((600, 96)).astype(np.float32); q = rng.standard_normal((40, 96)).astype(np.float32)
+    ix = Vamana.from_arrays(x, graph(600, 64), 1, DistanceType.L2)
+    for w, c in ((7, 19), (64, 64)):
+        ix.search_parameters.buffer_config = SearchBufferConfig(w, c); ix.search(q, 5)
+    print("minimal sanitize workload done"); sys.exit(0)
 for dim, R in ((17, 5), (96, 64), (300, 33)):
     n = 600
     x = rng.standard_normal((n, dim)).astype(np.float32); q = rng.standard_normal((40, dim)).astype(np.float32)
