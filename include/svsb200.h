@@ -159,7 +159,9 @@ int svsb200_get_counters(svsb200_index* index, size_t nq, uint32_t* hops, uint32
  * equivalent `evals` -- is what the HBM roofline of the kernel is computed from. */
 int svsb200_get_fetched(svsb200_index* index, size_t nq, uint32_t* fetched);
 /* Duration in milliseconds of the search kernel of the last svsb200_search* call on this
- * index (CUDA events on the launching stream; synchronises on the stop event). */
+ * index (CUDA events on the launching stream; synchronises on the stop event).  A host-buffer
+ * batch that was cut into pieces ("host_chunks") reports its last piece, from that piece's
+ * enqueue to its end -- i.e. including the time it waited for SMs behind the earlier pieces. */
 int svsb200_last_kernel_ms(svsb200_index* index, float* ms);
 /* Number of kernels this library launched so far in this process. */
 uint64_t svsb200_launch_count(void);
