@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define SVSB200_VERSION 200
+#define SVSB200_VERSION 201
 
 /* Element types: svs::DataType float32 / float16 / int8 / uint8 (lib/datatype.h). */
 enum { SVSB200_F32 = 0, SVSB200_F16 = 1, SVSB200_I8 = 2, SVSB200_U8 = 3 };
@@ -243,6 +243,15 @@ int svsb200_build_vamana(
     const void* vectors, int dtype, size_t n, size_t dim, size_t row_stride_bytes, int metric,
     float alpha, size_t graph_max_degree, size_t window_size, size_t max_candidate_pool_size,
     size_t prune_to, int device, uint32_t* graph_rows_out, uint32_t* entry_point_out);
+
+/* How svsb200_flat_search* will split a problem of `nq` queries over `n` base vectors on a device with `sm_count`
+ * SMs (introspection, host arithmetic only; nothing in the reference corresponds): `ctas` thread blocks are
+ * launched; the 128-query tiles are taken `share` at a time and the (row group, 256-row base tile) pairs form one
+ * row-major sequence cut into ctas / share equal segments, each walked by `share` blocks together;
+ * `lists_per_query` candidate lists of 33 entries reach the rescoring step.  `segment_begin` (optional,
+ * ctas / share + 1 entries) receives the first pair of every segment and the total. */
+int svsb200_flat_plan(size_t nq, size_t n, int sm_count, uint32_t* ctas, uint32_t* share, uint32_t* lists_per_query,
+                      uint64_t* segment_begin);
 
 /* Exact exhaustive (flat) search on the tensor cores.  Replaces: svs::Flat / FlatIndex::search
  * (include/svs/index/flat/flat.h:159,421-465): top-k of every query against all `n` base vectors inside `index`.

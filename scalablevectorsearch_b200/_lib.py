@@ -22,6 +22,7 @@ SYMBOLS = [
     "svsb200_merge_topk_device", "svsb200_exhaustive_device", "svsb200_lvq8_row_stride", "svsb200_lvq8_compress",
     "svsb200_index_create_multi", "svsb200_index_num_devices", "svsb200_search_cancellable", "svsb200_set_id_offset",
     "svsb200_search_sharded", "svsb200_build_vamana", "svsb200_flat_search_device", "svsb200_flat_search", "svsb200_index_assemble", "svsb200_toml_get", "svsb200_search_filtered", "svsb200_range_search", "svsb200_free", "svsb200_set_entry_points",
+    "svsb200_flat_plan",
 ]
 
 _lib = None
@@ -46,6 +47,8 @@ def lib() -> C.CDLL:
     l.svsb200_last_error.restype = C.c_char_p
     l.svsb200_launch_count.restype = C.c_uint64
     l.svsb200_device_sm.argtypes = [i32, C.POINTER(i32)]
+    l.svsb200_flat_plan.argtypes = [C.c_size_t, C.c_size_t, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                    C.POINTER(C.c_uint32), C.c_void_p]
     l.svsb200_index_create.argtypes = [vp, i32, sz, sz, sz, vp, sz, u32, i32, i32, vp, i32, C.POINTER(vp)]
     l.svsb200_index_destroy.argtypes = [vp]
     for name in ("size", "dimensions", "max_degree", "device_bytes"):

@@ -656,3 +656,21 @@ cudaError_t flat_move_rows(const void* src, void* dst, const uint32_t* idx, cons
 uint32_t flat_kc() { return FLAT_KC; }
 
 }  // namespace svsb200
+
+// How svsb200_flat_search* splits a problem (include/svsb200.h): host arithmetic only, so that the work split -- which the
+// kernel recomputes from the same inline functions -- can be checked without a device (tests/test_flat_plan.py).
+extern "C" int svsb200_flat_plan(size_t nq, size_t n, int sm_count, uint32_t* ctas, uint32_t* share, uint32_t* lists_per_query,
+                                 uint64_t* segment_begin) {
+    using namespace svsb200;
+    if (nq == 0 || n == 0 || sm_count <= 0 || !ctas || !share || !lists_per_query)
+        return set_error("svsb200_flat_plan: nq, n, sm_count must be positive and the outputs non-NULL");
+    if (nq > (size_t(1) << 31) || n > (size_t(1) << 31)) return set_error("svsb200_flat_plan: problem too large");
+    const uint32_t mtiles = uint32_t((nq + FLAT_BM - 1) / FLAT_BM), ntiles = uint32_t((n + FLAT_BN - 1) / FLAT_BN);
+    flat_plan(mtiles, ntiles, uint32_t(sm_count), ctas, share, lists_per_query);
+    if (segment_begin) {
+        const uint32_t nseg = *ctas / *share, ngroups = (mtiles + *share - 1) / *share;
+        const uint64_t total = uint64_t(ngroups) * ntiles;
+        for (uint32_t b = 0; b <= nseg; ++b) segment_begin[b] = flat_seg_begin(total, nseg, b);
+    }
+    return 0;
+}

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in header_symbols() if not hasattr(lib, s)]
     assert not missing, f"libsvsb200.so lacks {missing}"
     assert sorted(_lib.SYMBOLS) == header_symbols(), "python binding list out of sync with the header"
-    assert lib.svsb200_version() == 200
+    assert lib.svsb200_version() == 201
 
 
 def test_no_cpu_fallback_without_a_device():
